@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- separated audio-seconds per second of the DL4SS hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one pass of the hot path (waveform -> STFT features -> BLSTM 4x300 -> speaker attention
+masks -> mask x mixture -> iSTFT) over one batch of synthetic WSJ0-2mix-shaped mixtures
+(BASELINE.json configs[1]: TDAA_beta, 2 speakers, 5 s @ 8 kHz, batch 256 per GPU, fp32).
+`value` times the steps with the inputs resident in HBM; `e2e` times the same call from pinned host
+buffers (H2D of the waveforms, D2H of the separated waveforms inside the timed region).
+N > 1: one process per GPU (torchrun), utterances sharded by batch, no data-path collective
+(inference), weak scaling.  `--impl reference` times the CPU oracle (a Python-3 restatement of the
+reference, which is Python 2 + librosa and cannot run here) on the host cores, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+SR = 8000
+WORKLOAD = {'name': 'TDAA_beta 2-speaker attention-mask inference (BASELINE configs[1])',
+            'L': 40000, 'S': 2, 'hop': 128, 'n_fft': 256, 'cell': 'lstm', 'layers': 4, 'H': 300, 'E': 50,
+            'num_spk': 101, 'self_tune': True, 'complex_mask': False}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d.get('hbm_gbs', 6650.0), 'bf16_tflops': d.get('bf16_tflops', 1590.0),
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained', 1400.0), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_wave_batches(B, L, n_batches, device, seed):
+    """Synthetic mixtures shaped like the reference's: S sources, each -mean, /max|.|, +-2.5 dB gain,
+    summed (TDAA_beta/predata_fromList.py:146-177).  Built on the device (timing is data independent);
+    the parity tests use the speech-like generator of oracle/synth.py."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        mix = torch.zeros(B, L, device=device)
+        for s in range(WORKLOAD['S']):
+            x = torch.randn(B, L, device=device, generator=g)
+            x = x - x.mean(1, keepdim=True)
+            x = x / x.abs().amax(1, keepdim=True)
+            gain = 10.0 ** ((torch.rand(B, 1, device=device, generator=g) * 5.0 - 2.5) / 20.0)
+            mix += gain * x
+        out.append(mix.contiguous())
+    return out
+
+
+def build_model(device):
+    import dl4ss_b200 as d
+    W = WORKLOAD
+    torch.manual_seed(1)
+    d.config.HIDDEN_UNITS, d.config.EMBEDDING_SIZE = W['H'], W['E']
+    d.config.is_ComlexMask, d.config.is_SelfTune = W['complex_mask'], W['self_tune']
+    d.config.FRAME_SHIFT = W['hop']
+    T = 1 + W['L'] // W['hop']
+    F = W['n_fft'] // 2 + 1
+    mix = d.MIX_SPEECH(F, T, cell=W['cell'], num_layers=W['layers']).to(device)
+    emb = d.SPEECH_EMBEDDING(W['num_spk'], W['E'], 2).to(device)
+    att = d.ATTENTION(W['E'], 'dot').to(device)
+    adj = d.ADDJUST(2 * W['H'], W['E']).to(device)
+    return d.Separator(mix, emb, att, adj, W['n_fft'], W['hop'])
+
+
+def stage_times(sep, wav, idx, reps=3):
+    """Per-stage device time (CUDA events on the launching stream) of one step, for the roofline
+    lines; run outside the timed region."""
+    import dl4ss_b200 as d
+    from dl4ss_b200 import features, modules as M
+    W = WORKLOAD
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    names = ['stft', 'rnn_xproj', 'rnn_recurrent', 'query', 'emb_attn_mask', 'mask_istft']
+    acc = {n: [] for n in names}
+    lib = d.load_library()
+    for _ in range(reps):
+        t = {n: 0.0 for n in names}
+        with torch.no_grad():
+            e0, e1 = ev(), ev(); e0.record()
+            batch = sep.features(wav)
+            e1.record(); torch.cuda.synchronize(); t['stft'] += e0.elapsed_time(e1)
+            # encoder, split into its two kernel families
+            packed = sep.mix._packed
+            rnn = packed.rnn
+            x = batch['mix_feas']
+            B, T, _ = x.shape
+            G, H = 4 if W['cell'] == 'lstm' else 3, W['H']
+            from dl4ss_b200 import _lib
+            cell = _lib.CELL_LSTM if W['cell'] == 'lstm' else _lib.CELL_GRU
+            ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
+            ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+            xproj = torch.empty(B * T, 2 * G * H, device=x.device)
+            inp = x
+            for lw in packed.get():
+                e0, e1, e2 = ev(), ev(), ev(); e0.record()
+                M.linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
+                e1.record()
+                y = torch.empty(B, T, 2 * H, device=x.device)
+                rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
+                                             _lib.ptr(y), B, T, H, None, None, _lib.ptr(ws, torch.uint8), ws_bytes,
+                                             _lib.stream())
+                _lib.check(rc, 'rnn')
+                e2.record(); torch.cuda.synchronize()
+                t['rnn_xproj'] += e0.elapsed_time(e1); t['rnn_recurrent'] += e1.elapsed_time(e2)
+                inp = y
+            e0, e1 = ev(), ev(); e0.record()
+            q, _ = sep.queries(inp, idx)
+            e1.record(); torch.cuda.synchronize(); t['query'] += e0.elapsed_time(e1)
+            lin = sep.mix.Linear
+            e0, e1 = ev(), ev(); e0.record()
+            masks = M.emb_attn_mask(inp, lin.weight.detach(), lin.bias.detach(), q, x.shape[2], W['E'])
+            e1.record(); torch.cuda.synchronize(); t['emb_attn_mask'] += e0.elapsed_time(e1)
+            e0, e1 = ev(), ev(); e0.record()
+            features.mask_istft(masks, batch['mix_mag'], W['hop'])
+            e1.record(); torch.cuda.synchronize(); t['mask_istft'] += e0.elapsed_time(e1)
+        for n in names:
+            acc[n].append(t[n])
+    return {n: float(np.median(v)) for n, v in acc.items()}
+
+
+def algorithmic(B):
+    """Algorithmic bytes / flops per step (SURVEY 8d figures x utterances per launch)."""
+    W = WORKLOAD
+    L, S, hop = W['L'], W['S'], W['hop']
+    T, F, H, E = 1 + L // hop, W['n_fft'] // 2 + 1, W['H'], W['E']
+    G = 4 if W['cell'] == 'lstm' else 3
+    stft_bytes = B * (4 * L + 4 * T * F + 8 * T * F)                       # wav in, |X| and complex X out
+    istft_bytes = B * (4 * S * T * F + 8 * T * F + 4 * S * hop * (T - 1))  # masks + mixture in, wavs out
+    xproj_flops = sum(2.0 * B * T * (F if l == 0 else 2 * H) * 2 * G * H for l in range(W['layers']))
+    rec_flops = 2.0 * B * T * H * G * H * 2 * W['layers']
+    lin_flops = 2.0 * B * T * 2 * H * F * E
+    return {'stft_bytes': stft_bytes, 'istft_bytes': istft_bytes, 'xproj_flops': xproj_flops,
+            'rec_flops': rec_flops, 'emb_flops': lin_flops + 2.0 * B * S * T * F * E}
+
+
+def cpu_oracle_setup(n_utt, seed=1):
+    from oracle import modules_ref as mr, synth
+    W = WORKLOAD
+    T = 1 + W['L'] // W['hop']
+    F = W['n_fft'] // 2 + 1
+    torch.manual_seed(1)
+    rc = mr.RefConfig(HIDDEN_UNITS=W['H'], EMBEDDING_SIZE=W['E'], NUM_LAYERS=W['layers'],
+                      is_ComlexMask=W['complex_mask'])
+    mods = (mr.MIX_SPEECH(rc, F, T, W['cell'], W['layers']), mr.SPEECH_EMBEDDING(rc, W['num_spk'], W['E'], 2),
+            mr.ATTENTION(rc, W['E'], 'dot'), mr.ADDJUST(rc, 2 * W['H'], W['E']))
+    rng = np.random.RandomState(seed)
+    wav = rng.standard_normal((n_utt, W['L']))
+    idx = np.sort(rng.choice(W['num_spk'], (n_utt, W['S'])), axis=1)
+    return rc, mods, wav, idx
+
+
+def cpu_oracle_step(rc, mods, wav, idx):
+    """The reference's path on the CPU: per-utterance librosa-semantics STFTs (incl. the reference's
+    redundant second mixture STFT, TDAA_beta/predata_fromList.py:194-200), torch-CPU modules with
+    the S-fold expand+baddbmm attention, per-source numpy iSTFT."""
+    from oracle import modules_ref as mr, stft_ref as sr
+    W = WORKLOAD
+    feas, phase = [], []
+    for w in wav:
+        feas.append(np.transpose(np.abs(sr.stft_ref(w, W['n_fft'], W['hop']))))
+        phase.append(np.transpose(sr.stft_ref(w, W['n_fft'], W['hop'])))
+    feas = torch.from_numpy(np.array(feas, dtype=np.float32))
+    with torch.no_grad():
+        r = mr.forward_ref(rc, mods[0], mods[1], mods[2], mods[3], feas, idx)
+    return mr.reconstruct_ref(r, np.array(phase), W['hop'])
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_utt = args.ref_utts
+    rc, mods, wav, idx = cpu_oracle_setup(n_utt)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_oracle_step(rc, mods, wav, idx)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(rc, mods, wav, idx)
+    dt = time.perf_counter() - t0
+    audio_s = n_utt * WORKLOAD['L'] / SR * args.steps
+    v = audio_s / dt
+    line = {'impl': 'reference', 'metric': 'separated_audio_seconds_per_second', 'value': v, 'unit': 'audio-s/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(n_utt),
+            'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d utterances x 5 s per step (bounded sample of the batch-256 workload)' % n_utt},
+            'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(B):
+    W = WORKLOAD
+    return {'workload': W['name'], 'batch_per_gpu': B, 'utterance_s': W['L'] / SR, 'sample_rate': SR,
+            'n_fft': W['n_fft'], 'hop': W['hop'], 'speakers': W['S'],
+            'encoder': '%s %dx%d bidirectional' % (W['cell'].upper(), W['layers'], W['H']),
+            'embedding': W['E'], 'attention': 'dot + ADDJUST self-tune', 'mask': 'real sigmoid',
+            'l2': 'working set >> 126 MB L2 (xproj 769 MB/layer at B=256) and 4 rotating input batches'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='utterances per GPU per step')
+    ap.add_argument('--ref-utts', type=int, default=8, help='utterances per step of the CPU reference arm')
+    ap.add_argument('--cpu-baseline-utts', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    else:
+        torch.cuda.set_device(0)
+    device = torch.device('cuda', local_rank if world > 1 else 0)
+    import dl4ss_b200 as d
+    d.load_library()          # raises if the CUDA library is missing: no fallback
+
+    B, W = args.batch, WORKLOAD
+    sep = build_model(device)
+    wavs = make_wave_batches(B, W['L'], 4, device, seed=1 + rank)
+    g = torch.Generator().manual_seed(7 + rank)
+    idx = torch.sort(torch.stack([torch.randperm(W['num_spk'], generator=g)[:W['S']] for _ in range(B)]), 1)[0].to(device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for i in range(args.warmup):
+        sep.separate(wavs[i % len(wavs)], idx, check_index=False)
+    barrier()
+    sampler = ClockSampler(local_rank if world > 1 else 0)
+    if rank == 0:
+        sampler.start()
+    n0 = d.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = sep.separate(wavs[i % len(wavs)], idx, check_index=False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = d.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public call with HOST buffers ("e2e")
+    h_in = [w.cpu().pin_memory() for w in wavs]
+    h_idx = idx.cpu().pin_memory()
+    Lout = W['hop'] * (W['L'] // W['hop'])
+    h_out = torch.empty(B, W['S'], Lout, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(B, W['L'], device=device)
+    for i in range(2):
+        d_in.copy_(h_in[i % 4], non_blocking=True)
+        h_out.copy_(sep.separate(d_in, h_idx.to(device, non_blocking=True), check_index=False), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        d_in.copy_(h_in[i % 4], non_blocking=True)
+        h_out.copy_(sep.separate(d_in, h_idx.to(device, non_blocking=True), check_index=False), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device=device, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+
+    audio_s = world * B * W['L'] / SR * args.steps
+    value = audio_s / (ms * 1e-3)
+    e2e_v = audio_s / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        st = stage_times(sep, wavs[0], idx)
+        alg = algorithmic(B)
+        flops = {'rnn_xproj': alg['xproj_flops'], 'rnn_recurrent': alg['rec_flops'], 'emb_attn_mask': alg['emb_flops']}
+        dom = max(flops, key=lambda k: st[k])
+        n_launch = {'rnn_xproj': W['layers'], 'rnn_recurrent': W['layers'], 'emb_attn_mask': 1}[dom]
+        ach = flops[dom] / (st[dom] * 1e-3) / 1e12
+        roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
+                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
+                'launches_per_step': n_launch, 'ms_per_step': st[dom],
+                'note': 'fp32-exact math (CUDA-core FMA this round); fraction is against the bf16 tensor peak'}
+        stages = {}
+        for k, by in (('stft', alg['stft_bytes']), ('mask_istft', alg['istft_bytes'])):
+            a = by / (st[k] * 1e-3) / 1e9
+            stages[k] = {'bound': 'hbm', 'achieved': a, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': a / peaks['hbm_gbs'], 'ms': st[k], 'bytes': by}
+        for k in ('rnn_xproj', 'rnn_recurrent', 'emb_attn_mask'):
+            a = flops[k] / (st[k] * 1e-3) / 1e12
+            stages[k] = {'bound': 'tensor', 'achieved': a, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                         'frac': a / peaks['bf16_tflops_sustained'], 'ms': st[k], 'flops': flops[k]}
+        stages['query'] = {'ms': st['query']}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n_utt = args.cpu_baseline_utts
+            rc, mods, wav, cidx = cpu_oracle_setup(n_utt)
+            cpu_oracle_step(rc, mods, wav[:1], cidx[:1])
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+                cpu_oracle_step(rc, mods, wav, cidx)
+                reps += 1
+            dt = time.perf_counter() - t0
+            cpu = {'value': n_utt * W['L'] / SR * reps / dt, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+                   'sample': '%d reps of %d utterances x 5 s (same model/config, bounded sample)' % (reps, n_utt)}
+        bytes_in = B * W['L'] * 4 + idx.numel() * 8
+        bytes_out = B * W['S'] * Lout * 4
+        line = {'metric': 'separated_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': workload_config(B),
+                'e2e': {'value': e2e_v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': bytes_in,
+                        'd2h_bytes_per_step': bytes_out, 'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_stages': stages,
+                'cpu_baseline': cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,17 @@
+"""dl4ss_b200 -- B200-native (sm_100a) implementation of the DL4SS separation hot path.
+
+Public surface (names follow the reference, shincling/DL4SS):
+    config                                   the globals the modules read
+    MIX_SPEECH, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask      (modules.py)
+    stft_features, mask_istft, prepare_batch                         (features.py)
+    Separator, mask_loss                                             (pipeline.py)
+All compute goes through libdl4ss_b200.so (C ABI, include/dl4ss_b200.h); no CPU fallback.
+"""
+from . import config  # noqa: F401
+from ._lib import load as load_library, launch_count  # noqa: F401
+from .features import stft_features, mask_istft, prepare_batch, window_tensor  # noqa: F401
+from .modules import (MIX_SPEECH, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
+                      DeferredEmbedding, linear_fwd, rnn_forward, emb_attn_mask, crm_decompress)
+from .pipeline import Separator, mask_loss  # noqa: F401
+
+__version__ = '0.1.0'

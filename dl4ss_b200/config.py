@@ -1,0 +1,38 @@
+"""Config globals the separation modules read, with the reference's names and defaults.
+
+Mirror of the hot-path subset of TDAA_beta/config_WSJ0_dB.py:77-153 (== Torch_multi/config.py:98-143
+plus `is_ComlexMask` / `is_SelfTune`).  Like the reference it is a module of mutable globals:
+scripts do `import dl4ss_b200.config as config; config.BATCH_SIZE = 1`.
+Dataset paths, logging and the INI loader are outside the hot path and not mirrored.
+"""
+import numpy as np
+
+# components (TDAA_beta/config_WSJ0_dB.py:77-78)
+is_ComlexMask = False
+is_SelfTune = True
+
+HIDDEN_UNITS = 300          # Torch_multi/config.py:98
+NUM_LAYERS = 2              # :100
+EMBEDDING_SIZE = 50         # :102
+BATCH_SIZE = 16             # :110
+FRAME_RATE = 8000           # :112
+FRAME_LENGTH = int(0.032 * FRAME_RATE)   # 256, :114
+FRAME_SHIFT = int(0.016 * FRAME_RATE)    # 128, :116 (every reference config uses 128)
+MIN_MIX = 2
+MAX_MIX = 2
+MAX_LEN = FRAME_RATE * 5    # 40000, :129-130
+WINDOWS = FRAME_LENGTH      # :133 (replaced by the sine table when init_config() runs, :240)
+IS_LOG_SPECTRAL = False     # :143
+Out_Sep_Result = True
+
+# cRM constants (TDAA_beta/main_run_sstune_cRM_EvalVer.py:28-29)
+cRM_k = 10.0
+cRM_C = 0.1
+
+EPS_LOG = float(np.spacing(1))   # TDAA_beta/predata_fromList.py:192
+
+
+def sine_window(win_size=None):
+    """The window init_config() installs for the log-spectral mode (Torch_multi/config.py:238-240)."""
+    n = FRAME_LENGTH if win_size is None else win_size
+    return [np.sin(x_i * np.pi / n) for x_i in range(n)]

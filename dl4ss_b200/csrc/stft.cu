@@ -1,0 +1,358 @@
+// K1  dl4ss_stft_feat : frame + window + 256-pt FFT + |.| / log(|.|+eps) (+ complex spectrum)
+// K6  dl4ss_mask_istft: mask x mixture + Hermitian iFFT + window + overlap-add + normalise
+//
+// Both are HBM-bound stages: each waveform sample / spectrum bin crosses HBM once.
+// Frames are staged in shared memory so the 50-75 % frame overlap never re-reads HBM, two real
+// frames ride one complex transform (real/imag packing), and the 256-point transform runs on 16
+// lanes x 16 registers with one shared-memory transpose (fft256.cuh).
+#include "fft256.cuh"
+
+namespace dl4ss {
+
+constexpr int STFT_THREADS = 256;
+constexpr int STFT_GROUPS = STFT_THREADS / 16;   // 16-lane FFT groups per CTA
+constexpr int STFT_FT = 2 * STFT_GROUPS;         // frames per tile (two per group)
+constexpr int NFFT = 256;
+constexpr int NBIN = 129;
+
+// ------------------------------------------------------------------------------------ K1
+template <typename WavT>
+__global__ void __launch_bounds__(STFT_THREADS)
+stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt,
+               const float *__restrict__ window, int feat_mode, float eps, int conj,
+               float *__restrict__ feat, float2 *__restrict__ cplx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);                 // 256 float2
+    float2 *xch = tw + 256;                                            // groups * 272 float2
+    float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);   // 256
+    float *samples = win + NFFT;                                       // (FT-1)*hop + 256
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / tiles_per_utt;
+    const int tile = blockIdx.x - b * tiles_per_utt;
+    const int t0 = tile * STFT_FT;
+    const int nf = min(STFT_FT, T - t0);
+
+    fill_twiddles(tw, tid, STFT_THREADS);
+    win[tid] = window[tid];
+
+    // stage the tile's samples once: frame t spans signal [t*hop-128, t*hop+128), reflect-padded
+    {
+        const WavT *w = wav + (size_t)b * L;
+        const int s0 = t0 * hop - NFFT / 2;
+        const int ns = (nf - 1) * hop + NFFT;
+        for (int i = tid; i < ns; i += STFT_THREADS) {
+            int j = s0 + i;
+            j = (j < 0) ? -j : j;
+            j = (j >= L) ? 2 * (L - 1) - j : j;
+            samples[i] = (float)w[j];
+        }
+    }
+    __syncthreads();
+
+    const int g = tid >> 4, l16 = tid & 15;
+    const int fa = 2 * g, fb = 2 * g + 1;
+    const bool va = fa < nf, vb = fb < nf;
+
+    float2 v[16];
+    {
+        const float *sa = samples + (va ? fa : 0) * hop + l16;
+        const float *sb = samples + (vb ? fb : 0) * hop + l16;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            float w = win[l16 + 16 * n2];
+            v[n2] = make_float2(sa[16 * n2] * w, sb[16 * n2] * w);
+        }
+    }
+    fft256_group<false>(v, l16, xch + g * DL4SS_XCH_FLOAT2, tw);
+
+    // split Z = FFT(xa + i*xb) into the two real-input spectra:
+    //   XA[k] = (Z[k] + conj(Z[256-k]))/2 ,  XB[k] = (Z[k] - conj(Z[256-k]))/(2i)
+    // lane holds Z[16*k1+l16] in v[k1]; Z[256-k] lives in lane (16-l16)&15, register 15-k1
+    // (lane 0: own register (16-k1)&15).
+    const size_t rowa = ((size_t)b * T + t0 + fa) * NBIN;
+    const size_t rowb = rowa + NBIN;
+    const int src = (16 - l16) & 15;
+    const float sgn = conj ? -1.0f : 1.0f;
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        float2 z = v[k1];
+        float px = __shfl_sync(0xffffffffu, v[15 - k1].x, src, 16);
+        float py = __shfl_sync(0xffffffffu, v[15 - k1].y, src, 16);
+        if (l16 == 0) {
+            px = v[(16 - k1) & 15].x;
+            py = v[(16 - k1) & 15].y;
+        }
+        float2 xa = make_float2(0.5f * (z.x + px), 0.5f * (z.y - py));
+        float2 xb = make_float2(0.5f * (z.y + py), -0.5f * (z.x - px));
+        const int k = 16 * k1 + l16;
+        if (feat_mode != DL4SS_FEAT_NONE) {
+            float ma = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y));
+            float mb = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y));
+            if (feat_mode == DL4SS_FEAT_LOG) {
+                ma = logf(ma + eps);
+                mb = logf(mb + eps);
+            }
+            if (va) feat[rowa + k] = ma;
+            if (vb) feat[rowb + k] = mb;
+        }
+        if (cplx != nullptr) {
+            if (va) cplx[rowa + k] = make_float2(xa.x, sgn * xa.y);
+            if (vb) cplx[rowb + k] = make_float2(xb.x, sgn * xb.y);
+        }
+    }
+    if (l16 == 0) {   // Nyquist bin: Z[128] = XA[128] + i*XB[128], both real
+        float xa = v[8].x, xb = v[8].y;
+        if (feat_mode != DL4SS_FEAT_NONE) {
+            float ma = fabsf(xa), mb = fabsf(xb);
+            if (feat_mode == DL4SS_FEAT_LOG) {
+                ma = logf(ma + eps);
+                mb = logf(mb + eps);
+            }
+            if (va) feat[rowa + 128] = ma;
+            if (vb) feat[rowb + 128] = mb;
+        }
+        if (cplx != nullptr) {
+            if (va) cplx[rowa + 128] = make_float2(xa, 0.0f);
+            if (vb) cplx[rowb + 128] = make_float2(xb, 0.0f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ K6
+// One CTA reconstructs `bpt` hop-blocks of every source of one utterance.  It transforms the
+// frames that touch those blocks (a leading halo of ceil(256/hop)-1 frames is recomputed by the
+// neighbouring tile instead of exchanged), parks windowed frames in shared memory, then every
+// thread sums the <= ceil(256/hop) overlapping frames of its output samples and divides by the
+// window sum-square envelope (librosa.istft semantics).
+template <int MASK_KIND>
+__global__ void __launch_bounds__(STFT_THREADS)
+istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec, int S, int T,
+                int hop, int bpt, int tiles_per_utt, int max_frames,
+                const float *__restrict__ window, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *xch = tw + 256;
+    float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);
+    float *ybuf = win + NFFT;                                          // max_frames*S*256
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / tiles_per_utt;
+    const int tile = blockIdx.x - b * tiles_per_utt;
+    const int Lout = hop * (T - 1);
+    // padded sample coordinates m = n + 128
+    const int m_lo = NFFT / 2 + tile * bpt * hop;
+    const int m_hi = min(m_lo + bpt * hop, NFFT / 2 + Lout);
+    int t_lo = (m_lo - (NFFT - 1) + hop - 1) / hop;          // ceil((m_lo-255)/hop), m_lo >= 128
+    if (m_lo - (NFFT - 1) < 0) t_lo = 0;
+    const int t_hi = min(T - 1, (m_hi - 1) / hop);
+    const int nfr = t_hi - t_lo + 1;
+    const int nitems = nfr * S;
+    const int npairs = (nitems + 1) >> 1;
+
+    fill_twiddles(tw, tid, STFT_THREADS);
+    win[tid] = window[tid] * (1.0f / NFFT);     // fold the 1/N of the inverse transform
+    __syncthreads();
+
+    const int g = tid >> 4, l16 = tid & 15;
+    const int src = (16 - l16) & 15;
+    const int rounds = (npairs + STFT_GROUPS - 1) / STFT_GROUPS;
+    for (int r = 0; r < rounds; ++r) {
+        const int p = r * STFT_GROUPS + g;
+        const int ia = 2 * p, ib = 2 * p + 1;
+        const bool va = ia < nitems, vb = ib < nitems;
+        const int ta = t_lo + (va ? ia / S : 0), sa = va ? ia % S : 0;
+        const int tb = t_lo + (vb ? ib / S : 0), sb = vb ? ib % S : 0;
+
+        float2 pa[8], pb[8], pa_n = make_float2(0.f, 0.f), pb_n = make_float2(0.f, 0.f);
+        if (MASK_KIND == DL4SS_MASK_NONE) {
+            const float2 *ra = spec + (((size_t)b * S + sa) * T + ta) * NBIN;
+            const float2 *rb = spec + (((size_t)b * S + sb) * T + tb) * NBIN;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                pa[m] = va ? ra[16 * m + l16] : make_float2(0.f, 0.f);
+                pb[m] = vb ? rb[16 * m + l16] : make_float2(0.f, 0.f);
+            }
+            if (l16 == 0) {
+                if (va) pa_n = ra[128];
+                if (vb) pb_n = rb[128];
+            }
+        } else {
+            const float2 *xa = spec + ((size_t)b * T + ta) * NBIN;
+            const float2 *xb = spec + ((size_t)b * T + tb) * NBIN;
+            const size_t ma = (((size_t)b * S + sa) * T + ta) * NBIN;
+            const size_t mb = (((size_t)b * S + sb) * T + tb) * NBIN;
+            float2 xva[8], xvb[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                xva[m] = va ? xa[16 * m + l16] : make_float2(0.f, 0.f);
+                xvb[m] = vb ? xb[16 * m + l16] : make_float2(0.f, 0.f);
+            }
+            if (MASK_KIND == DL4SS_MASK_REAL) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    float ka = va ? mask[ma + 16 * m + l16] : 0.f;
+                    float kb = vb ? mask[mb + 16 * m + l16] : 0.f;
+                    pa[m] = make_float2(ka * xva[m].x, ka * xva[m].y);
+                    pb[m] = make_float2(kb * xvb[m].x, kb * xvb[m].y);
+                }
+                if (l16 == 0) {
+                    if (va) { float k = mask[ma + 128]; float2 x = xa[128]; pa_n = make_float2(k * x.x, k * x.y); }
+                    if (vb) { float k = mask[mb + 128]; float2 x = xb[128]; pb_n = make_float2(k * x.x, k * x.y); }
+                }
+            } else {
+                const float2 *cma = reinterpret_cast<const float2 *>(mask) + ma;
+                const float2 *cmb = reinterpret_cast<const float2 *>(mask) + mb;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    float2 ka = va ? cma[16 * m + l16] : make_float2(0.f, 0.f);
+                    float2 kb = vb ? cmb[16 * m + l16] : make_float2(0.f, 0.f);
+                    // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
+                    pa[m] = make_float2(ka.x * xva[m].x - ka.y * xva[m].y, ka.x * xva[m].y + ka.y * xva[m].x);
+                    pb[m] = make_float2(kb.x * xvb[m].x - kb.y * xvb[m].y, kb.x * xvb[m].y + kb.y * xvb[m].x);
+                }
+                if (l16 == 0) {
+                    if (va) { float2 k = cma[128]; float2 x = xa[128]; pa_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+                    if (vb) { float2 k = cmb[128]; float2 x = xb[128]; pb_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+                }
+            }
+        }
+        if (l16 == 0) {   // DC bin: irfft ignores the imaginary part
+            pa[0].y = 0.f;
+            pb[0].y = 0.f;
+        }
+        // Z[k] = A[k] + i*B[k] for k <= 128 ; Z[256-k] = conj(A[k]) + i*conj(B[k])
+        float2 v[16], c[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            v[m] = make_float2(pa[m].x - pb[m].y, pa[m].y + pb[m].x);
+            c[m] = make_float2(pa[m].x + pb[m].y, pb[m].x - pa[m].y);
+        }
+#pragma unroll
+        for (int m = 8; m < 16; ++m) {
+            float cx = __shfl_sync(0xffffffffu, c[15 - m].x, src, 16);
+            float cy = __shfl_sync(0xffffffffu, c[15 - m].y, src, 16);
+            if (l16 == 0) {
+                if (m == 8) { cx = pa_n.x; cy = pb_n.x; }
+                else { cx = c[16 - m].x; cy = c[16 - m].y; }
+            }
+            v[m] = make_float2(cx, cy);
+        }
+        fft256_group<true>(v, l16, xch + g * DL4SS_XCH_FLOAT2, tw);
+        float *ya = ybuf + (size_t)ia * NFFT;
+        float *yb = ybuf + (size_t)ib * NFFT;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int n = 16 * n1 + l16;
+            const float w = win[n];
+            if (va) ya[n] = v[n1].x * w;
+            if (vb) yb[n] = v[n1].y * w;
+        }
+    }
+    __syncthreads();
+
+    // overlap-add + window-sum-square normalisation + trim
+    const int span = m_hi - m_lo;
+    const float wscale = (float)NFFT * (float)NFFT;    // win[] carries 1/N
+    for (int s = 0; s < S; ++s) {
+        float *o = out + ((size_t)b * S + s) * Lout + (m_lo - NFFT / 2);
+        for (int i = tid; i < span; i += STFT_THREADS) {
+            const int m = m_lo + i;
+            int t1 = min(t_hi, m / hop);
+            float acc = 0.f, env = 0.f;
+            for (int t = t1; t >= t_lo && m - t * hop < NFFT; --t) {
+                const int n = m - t * hop;
+                acc += ybuf[(size_t)((t - t_lo) * S + s) * NFFT + n];
+                const float w = win[n];
+                env = fmaf(w, w, env);
+            }
+            env *= wscale;
+            o[i] = (env > 1.17549435e-38f) ? acc / env : acc;
+        }
+    }
+}
+
+}  // namespace dl4ss
+
+using namespace dl4ss;
+
+extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int n_fft, int hop,
+                               const float *window, int feat_mode, float eps, int conj,
+                               float *feat_out, float *cplx_out, void *stream) {
+    DL4SS_CHECK_ARG(wav && window, "stft_feat: null wav/window");
+    DL4SS_CHECK_ARG(B >= 0 && L > n_fft / 2, "stft_feat: need B>=0 and L > n_fft/2 (reflect pad), got B=%d L=%d", B, L);
+    DL4SS_CHECK_ARG(hop >= 1 && hop <= n_fft, "stft_feat: hop must be in [1,n_fft], got %d", hop);
+    DL4SS_CHECK_ARG(feat_mode >= DL4SS_FEAT_NONE && feat_mode <= DL4SS_FEAT_LOG, "stft_feat: bad feat_mode %d", feat_mode);
+    DL4SS_CHECK_ARG(feat_mode == DL4SS_FEAT_NONE || feat_out, "stft_feat: feat_out is null");
+    DL4SS_CHECK_ARG(feat_out || cplx_out, "stft_feat: no output requested");
+    DL4SS_CHECK_ARG(wav_dtype == DL4SS_WAV_F32 || wav_dtype == DL4SS_WAV_F64, "stft_feat: bad wav_dtype %d", wav_dtype);
+    if (n_fft != NFFT) {
+        set_error("stft_feat: this build has the 256-point transform only (n_fft=%d)", n_fft);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0) return DL4SS_OK;
+    const int T = 1 + L / hop;
+    const int tiles = cdiv(T, STFT_FT);
+    const size_t smem = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
+                        NFFT * sizeof(float) + ((STFT_FT - 1) * (size_t)hop + NFFT) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long grid = (long long)B * tiles;
+    DL4SS_CHECK_ARG(grid < (1ll << 31), "stft_feat: grid too large");
+    if (wav_dtype == DL4SS_WAV_F32) {
+        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stft256_kernel<float><<<(unsigned)grid, STFT_THREADS, smem, st>>>(
+            (const float *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
+    } else {
+        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stft256_kernel<double><<<(unsigned)grid, STFT_THREADS, smem, st>>>(
+            (const double *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
+    }
+    DL4SS_LAUNCH_CHECK("stft256_kernel");
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *spec, int B, int S,
+                                int T, int n_fft, int hop, const float *window, float *wav_out,
+                                void *stream) {
+    DL4SS_CHECK_ARG(spec && window && wav_out, "mask_istft: null spec/window/out");
+    DL4SS_CHECK_ARG(mask_kind >= DL4SS_MASK_NONE && mask_kind <= DL4SS_MASK_COMPLEX, "mask_istft: bad mask_kind %d", mask_kind);
+    DL4SS_CHECK_ARG(mask_kind == DL4SS_MASK_NONE || mask, "mask_istft: mask is null");
+    DL4SS_CHECK_ARG(B >= 0 && S >= 1 && T >= 1, "mask_istft: bad B/S/T %d/%d/%d", B, S, T);
+    DL4SS_CHECK_ARG(hop >= 1 && hop <= n_fft, "mask_istft: hop must be in [1,n_fft], got %d", hop);
+    if (n_fft != NFFT) {
+        set_error("mask_istft: this build has the 256-point transform only (n_fft=%d)", n_fft);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0 || T == 1) return DL4SS_OK;     // hop*(T-1) == 0 samples
+    const int halo = (NFFT - 1) / hop;         // frames before the first block's own frame
+    const int nblocks = T - 1;
+    // frames per CTA: aim at 32 (frame,source) items = one round of 16 two-frame groups
+    int max_items = (S <= 16) ? 32 : 2 * S;
+    int bpt = max_items / S - halo;
+    while (bpt < 1) { max_items += 32; bpt = max_items / S - halo; }
+    if (bpt > nblocks) bpt = nblocks;
+    const int tiles = cdiv(nblocks, bpt);
+    bpt = cdiv(nblocks, tiles);
+    const int max_frames = bpt + halo + 1;
+    const size_t smem = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
+                        NFFT * sizeof(float) + (size_t)max_frames * S * NFFT * sizeof(float);
+    if (smem > 220 * 1024) {
+        set_error("mask_istft: S=%d hop=%d needs %zu B of shared memory", S, hop, smem);
+        return DL4SS_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long grid = (long long)B * tiles;
+    DL4SS_CHECK_ARG(grid < (1ll << 31), "mask_istft: grid too large");
+#define LAUNCH_ISTFT(KIND)                                                                             \
+    do {                                                                                               \
+        DL4SS_CUDA(cudaFuncSetAttribute(istft256_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        istft256_kernel<KIND><<<(unsigned)grid, STFT_THREADS, smem, st>>>(                             \
+            mask, (const float2 *)spec, S, T, hop, bpt, tiles, max_frames, window, wav_out);           \
+    } while (0)
+    if (mask_kind == DL4SS_MASK_NONE) LAUNCH_ISTFT(DL4SS_MASK_NONE);
+    else if (mask_kind == DL4SS_MASK_REAL) LAUNCH_ISTFT(DL4SS_MASK_REAL);
+    else LAUNCH_ISTFT(DL4SS_MASK_COMPLEX);
+#undef LAUNCH_ISTFT
+    DL4SS_LAUNCH_CHECK("istft256_kernel");
+    return DL4SS_OK;
+}

@@ -1,0 +1,375 @@
+"""The reference's separation modules, same names / constructor arguments / forward layouts /
+state-dict keys, running on the dl4ss_b200 CUDA kernels.
+
+  MIX_SPEECH        TDAA_beta/main_run_sstune_EvalVer.py:277-303 (LSTM) ;
+                    TDAA_beta/main_run_sstune_cRM_EvalVer.py:340-365 (GRU) ;
+                    Torch_multi/test_multi_labels_speech.py:212-233 (LSTM 2x300)
+  ATTENTION         TDAA_beta/main_run_sstune_EvalVer.py:199-242 ; cRM ...cRM_EvalVer.py:247-271
+  SPEECH_EMBEDDING  TDAA_beta/main_run_sstune_EvalVer.py:348-361 ; cRM ...cRM_EvalVer.py:390-406
+  ADDJUST           TDAA_beta/main_run_sstune_EvalVer.py:363-377 ; cRM ...cRM_EvalVer.py:408-426
+  top_k_mask        TDAA_beta/main_run_sstune_EvalVer.py:390-405
+
+Parameters live in ordinary torch containers (`self.layer = nn.LSTM(...)`, `self.Linear`, ...) so
+`state_dict()` / `load_state_dict()` are key-compatible with the reference's checkpoints
+(`layer.weight_ih_l0`, ..., `Linear.weight`, `Linear_1.weight`, ...); the containers' own forward
+is never called -- every forward goes through the C ABI (dl4ss_b200._lib) and raises if the CUDA
+library is missing.  Differences from the reference that do not change results: B is taken from
+the input (the reference reads config.BATCH_SIZE inside forward), and MIX_SPEECH may hand
+ATTENTION a `DeferredEmbedding` instead of the 8 MB/utterance [B,T,F,E] tensor (see below).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from . import config
+
+
+# ----------------------------------------------------------------------------- low-level ops
+def linear_fwd(x2d, weight, bias=None, act='none', out=None):
+    """act(x2d[M,K] @ weight[N,K]^T + bias) on the fp32 CUDA-core GEMM."""
+    lib = _lib.load()
+    M, K = x2d.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x2d.device, dtype=torch.float32)
+    a = {'none': _lib.ACT_NONE, 'tanh': _lib.ACT_TANH, 'sigmoid': _lib.ACT_SIGMOID}[act]
+    rc = lib.dl4ss_linear_fwd(_lib.ptr(x2d, name='x'), x2d.stride(0), _lib.ptr(weight, name='weight'),
+                              weight.stride(0), _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0),
+                              M, N, K, a, _lib.stream())
+    _lib.check(rc, 'dl4ss_linear_fwd')
+    return out
+
+
+class _PackedRNN(object):
+    """Per-layer operands of the recurrent kernel, rebuilt only when a parameter changes."""
+
+    def __init__(self, rnn):
+        self.rnn = rnn
+        self.key = None
+        self.layers = None
+
+    def get(self):
+        rnn = self.rnn
+        key = tuple((p.data_ptr(), p._version) for p in rnn.parameters())
+        if key == self.key:
+            return self.layers
+        H = rnn.hidden_size
+        gru = isinstance(rnn, nn.GRU)
+        layers = []
+        with torch.no_grad():
+            for l in range(rnn.num_layers):
+                wih, bias, whh, bhn = [], [], [], []
+                for suf in ('', '_reverse'):
+                    w_ih = getattr(rnn, 'weight_ih_l%d%s' % (l, suf))
+                    w_hh = getattr(rnn, 'weight_hh_l%d%s' % (l, suf))
+                    b_ih = getattr(rnn, 'bias_ih_l%d%s' % (l, suf))
+                    b_hh = getattr(rnn, 'bias_hh_l%d%s' % (l, suf))
+                    wih.append(w_ih)
+                    whh.append(w_hh)
+                    if gru:      # n-gate: b_hn stays inside r*(W_hn h + b_hn)
+                        b = b_ih.clone()
+                        b[:2 * H] += b_hh[:2 * H]
+                        bias.append(b)
+                        bhn.append(b_hh[2 * H:])
+                    else:
+                        bias.append(b_ih + b_hh)
+                layers.append({
+                    'wih': torch.cat(wih, 0).contiguous().float(),
+                    'bias': torch.cat(bias, 0).contiguous().float(),
+                    'whh': torch.stack(whh, 0).contiguous().float(),
+                    'bhn': torch.stack(bhn, 0).contiguous().float() if gru else None,
+                })
+        self.key, self.layers = key, layers
+        return layers
+
+
+def rnn_forward(packed, x, save=None):
+    """Bidirectional multi-layer LSTM/GRU forward, batch_first, zero initial state.
+    x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward."""
+    lib = _lib.load()
+    rnn = packed.rnn
+    gru = isinstance(rnn, nn.GRU)
+    cell = _lib.CELL_GRU if gru else _lib.CELL_LSTM
+    G = 3 if gru else 4
+    H = rnn.hidden_size
+    B, T, _ = x.shape
+    dev = x.device
+    ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    inp = x.contiguous()
+    xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
+    for lw in packed.get():
+        linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
+        y = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
+        gates = cells = None
+        if save is not None:
+            gates = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
+            cells = torch.empty(B, T, 2, H, device=dev, dtype=torch.float32)
+        rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
+                                     _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                     _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_layer_fwd')
+        if save is not None:
+            save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
+        inp = y
+    return inp
+
+
+def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=True):
+    """Fused Linear+tanh -> dot attention -> masks (K4).
+    h [B,T,K], weight [F*E,K], bias [F*E], query [B,S,E|2E] -> [B,S,T,F] (or [B,S,T,F,2])."""
+    lib = _lib.load()
+    B, T, K = h.shape
+    S = query.shape[1]
+    dev = h.device
+    mode = _lib.ATT_DOT_CRM if complex_mask else _lib.ATT_DOT
+    out = torch.empty((B, S, T, F, 2) if complex_mask else (B, S, T, F), device=dev, dtype=torch.float32)
+    ws_bytes = int(lib.dl4ss_emb_attn_mask_workspace_bytes(B, T, F, E))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    rc = lib.dl4ss_emb_attn_mask_fwd(_lib.ptr(h, name='h'), _lib.ptr(weight, name='weight'),
+                                     _lib.ptr(bias, name='bias'), _lib.ptr(query, name='query'),
+                                     B, T, F, E, K, S, mode, float(config.cRM_k),
+                                     float(config.cRM_C if decompress else 0.0), _lib.ptr(out),
+                                     _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
+    _lib.check(rc, 'dl4ss_emb_attn_mask_fwd')
+    return out
+
+
+def crm_decompress(att):
+    """-1/C * log((K-m)/(K+m))  (TDAA_beta/main_run_sstune_cRM_EvalVer.py:512); plain torch glue,
+    only used when a caller keeps the reference's two-step form."""
+    return -1 / config.cRM_C * torch.log((config.cRM_k - att) / (config.cRM_k + att))
+
+
+# ----------------------------------------------------------------------------- deferred tensor
+class DeferredEmbedding(object):
+    """Stand-in for MIX_SPEECH's [B,T,F,E] output that is never written to HBM.
+
+    It answers the shape calls the reference's glue makes on that tensor
+    (`.view(B,1,T,F,E).expand(B,S,T,F,E).contiguous().view(-1,T,F,E)`,
+    TDAA_beta/main_run_sstune_EvalVer.py:453-455) and is consumed by ATTENTION.forward, which then
+    runs the fused Linear+tanh+attention kernel on the encoder output.  `.materialize()` returns
+    the real tensor (costing the 8 MB/utterance the reference always pays)."""
+
+    def __init__(self, hidden, weight, bias, F, E, shape=None):
+        self.hidden, self.weight, self.bias = hidden, weight, bias
+        self.F, self.E = F, E
+        B, T, _ = hidden.shape
+        self.base = (B, T, F, E)
+        self._shape = tuple(shape) if shape is not None else self.base
+
+    def _like(self, shape):
+        shape = list(shape)
+        n = int(np.prod(self.base))
+        if -1 in shape:
+            known = int(np.prod([s for s in shape if s != -1]))
+            total = int(np.prod(self._shape))
+            shape[shape.index(-1)] = total // known
+        if int(np.prod(shape)) % n != 0 or tuple(shape[-3:]) != self.base[1:]:
+            raise RuntimeError('DeferredEmbedding only supports the [B(,S),T,F,E] reshapes of the '
+                               'reference glue; call .materialize() for anything else')
+        return DeferredEmbedding(self.hidden, self.weight, self.bias, self.F, self.E, shape)
+
+    def view(self, *shape):
+        return self._like(shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape)
+
+    reshape = view
+
+    def expand(self, *shape):
+        return self._like(shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape)
+
+    def contiguous(self):
+        return self
+
+    def size(self, dim=None):
+        return torch.Size(self._shape) if dim is None else self._shape[dim]
+
+    @property
+    def shape(self):
+        return torch.Size(self._shape)
+
+    def dim(self):
+        return len(self._shape)
+
+    @property
+    def copies(self):
+        """S of the expand: how many speaker queries share each utterance's embedding."""
+        return int(np.prod(self._shape)) // int(np.prod(self.base))
+
+    def materialize(self):
+        B, T, F, E = self.base
+        out = linear_fwd(self.hidden.view(B * T, -1), self.weight, self.bias, 'tanh').view(B, T, F, E)
+        S = self.copies
+        if S > 1:
+            out = out.view(B, 1, T, F, E).expand(B, S, T, F, E).contiguous()
+        return out.view(self._shape)
+
+
+# ----------------------------------------------------------------------------- modules
+class MIX_SPEECH(nn.Module):
+    """Mixture encoder: bidirectional LSTM/GRU -> Linear(2H -> F*E) -> tanh -> [B,T,F,E].
+
+    MIX_SPEECH(input_fre, mix_speech_len) as in the reference; extra keyword arguments select the
+    variant the different reference scripts hard-code: cell 'lstm' | 'gru', num_layers (default
+    config.NUM_LAYERS; the TDAA LSTM scripts hard-code 4), return_hidden (TDAA variants return
+    `(out, rnn_output)`, Torch_multi returns `out`), fused (hand ATTENTION a DeferredEmbedding)."""
+
+    def __init__(self, input_fre, mix_speech_len, cell='lstm', num_layers=None, return_hidden=True, fused=True):
+        super(MIX_SPEECH, self).__init__()
+        self.input_fre = input_fre
+        self.mix_speech_len = mix_speech_len
+        self.return_hidden = return_hidden
+        self.fused = fused
+        rnn = {'lstm': nn.LSTM, 'gru': nn.GRU}[cell]
+        self.layer = rnn(input_size=input_fre, hidden_size=config.HIDDEN_UNITS,
+                         num_layers=config.NUM_LAYERS if num_layers is None else num_layers,
+                         batch_first=True, bidirectional=True)
+        self.Linear = nn.Linear(2 * config.HIDDEN_UNITS, self.input_fre * config.EMBEDDING_SIZE)
+        self._packed = _PackedRNN(self.layer)
+
+    def encode(self, x):
+        return rnn_forward(self._packed, x)
+
+    def forward(self, x):
+        B, T, F = x.shape
+        xx = self.encode(x)
+        E = self.Linear.out_features // self.input_fre
+        if self.fused:
+            out = DeferredEmbedding(xx, self.Linear.weight.detach(), self.Linear.bias.detach(), F, E)
+        else:
+            out = linear_fwd(xx.view(B * T, -1), self.Linear.weight.detach(), self.Linear.bias.detach(),
+                             'tanh').view(B, T, F, E)
+        return (out, xx) if self.return_hidden else out
+
+
+class ATTENTION(nn.Module):
+    """ATTENTION(hidden_size, mode='dot'|'align').forward(mix_hidden[N,T,F,E], query[N,E|2E]).
+
+    Returns mask [N,T,F]; with config.is_ComlexMask, K*tanh(.) pairs [N,T,F,2] (decompression is
+    the caller's next line in the reference, kept that way here).  Linear_1/2/3 exist in every
+    mode, as in the reference, so checkpoints load."""
+
+    def __init__(self, hidden_size, mode='dot'):
+        super(ATTENTION, self).__init__()
+        self.hidden_size = hidden_size
+        self.align_hidden_size = hidden_size
+        self.mode = mode
+        self.Linear_1 = nn.Linear(self.hidden_size, self.align_hidden_size, bias=False)
+        self.Linear_2 = nn.Linear(hidden_size, self.align_hidden_size, bias=False)
+        self.Linear_3 = nn.Linear(self.align_hidden_size, 1, bias=False)
+
+    def forward(self, mix_hidden, query):
+        lib = _lib.load()
+        cplx = bool(config.is_ComlexMask)
+        E = self.hidden_size
+        if self.mode == 'dot':
+            if isinstance(mix_hidden, DeferredEmbedding):
+                B, T, F, _ = mix_hidden.base
+                S = mix_hidden.copies
+                q = query.contiguous().view(B, S, -1)
+                out = emb_attn_mask(mix_hidden.hidden, mix_hidden.weight, mix_hidden.bias, q, F, E,
+                                    complex_mask=cplx, decompress=False)
+                return out.view((B * S, T, F, 2) if cplx else (B * S, T, F))
+            N, T, F, _ = mix_hidden.shape
+            mix_hidden = mix_hidden.contiguous()
+            q = query.contiguous().view(N, 1, -1)
+            out = torch.empty((N, T, F, 2) if cplx else (N, T, F), device=mix_hidden.device, dtype=torch.float32)
+            rc = lib.dl4ss_attn_dot_fwd(_lib.ptr(mix_hidden, name='mix_hidden'), T * F * E, _lib.ptr(q, name='query'),
+                                        N, 1, T * F, E, _lib.ATT_DOT_CRM if cplx else _lib.ATT_DOT,
+                                        float(config.cRM_k), 0.0, _lib.ptr(out), _lib.stream())
+            _lib.check(rc, 'dl4ss_attn_dot_fwd')
+            return out
+        elif self.mode == 'align':
+            if cplx:
+                # the reference's cRM+align branch never fills `masks` (cRM_EvalVer.py:292-300)
+                raise IndexError('cRM + align attention is undefined in the reference')
+            if isinstance(mix_hidden, DeferredEmbedding):
+                mix_hidden = mix_hidden.materialize()
+            N, T, F, _ = mix_hidden.shape
+            a = linear_fwd(mix_hidden.contiguous().view(-1, E), self.Linear_1.weight.detach()).view(N, T * F, -1)
+            qq = linear_fwd(query.contiguous().view(N, E), self.Linear_2.weight.detach()).view(N, 1, -1)
+            s = torch.tanh(a + qq)
+            en = linear_fwd(s.view(-1, self.align_hidden_size), self.Linear_3.weight.detach(), None, 'sigmoid')
+            return en.view(N, T, F)
+        else:
+            raise IndexError('NO this attention methods.')
+
+
+def _speaker_query(h, table, idx, wadj, residual):
+    lib = _lib.load()
+    dev = table.device
+    if idx is not None:
+        B, S = idx.shape
+        EQ = table.shape[1]
+        num = table.shape[0]
+    else:
+        B, S, EQ = table.shape
+        num = 1
+    q = torch.empty(B, S, EQ, device=dev, dtype=torch.float32)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    T = C = 1
+    if h is not None:
+        _, T, C = h.shape
+    rc = lib.dl4ss_speaker_query_fwd(_lib.ptr(h, name='hidden'), B, T, C, _lib.ptr(table, name='table'), num, EQ,
+                                     _lib.ptr(idx, torch.int64, 'idx'), S, _lib.ptr(wadj, name='adjust weight'),
+                                     int(residual), _lib.ptr(q), None, _lib.ptr(err, torch.int32), _lib.stream())
+    _lib.check(rc, 'dl4ss_speaker_query_fwd')
+    return q, err
+
+
+class SPEECH_EMBEDDING(nn.Module):
+    """SPEECH_EMBEDDING(num_labels, embedding_size, max_num_channel).forward(input, mask_idx)
+    -> [B,S,E] (2E wide when config.is_ComlexMask).  `input` is ignored, as in the reference."""
+
+    def __init__(self, num_labels, embedding_size, max_num_channel):
+        super(SPEECH_EMBEDDING, self).__init__()
+        self.num_all = num_labels
+        self.emb_size = embedding_size
+        self.max_num_out = max_num_channel
+        if not config.is_ComlexMask:
+            self.layer = nn.Embedding(num_labels, embedding_size)
+        else:
+            self.layer = nn.Embedding(num_labels, 2 * embedding_size)
+
+    def index_tensor(self, mask_idx):
+        if torch.is_tensor(mask_idx):
+            return mask_idx.to(device=self.layer.weight.device, dtype=torch.int64).contiguous()
+        return torch.from_numpy(np.array(mask_idx, dtype=np.int64)).to(self.layer.weight.device)
+
+    def forward(self, input, mask_idx):
+        idx = self.index_tensor(mask_idx)
+        q, err = _speaker_query(None, self.layer.weight.detach(), idx, None, 1)
+        if int(err.item()):
+            raise IndexError('index out of range in self')     # nn.Embedding's error
+        return q
+
+
+class ADDJUST(nn.Module):
+    """ADDJUST(hidden_units, embedding_size).forward(input_hidden[B,T,2H], prob_emb[B,S,E])
+    -> Linear([mean_T(input_hidden) ; prob_emb]) (no bias); the caller adds the residual."""
+
+    def __init__(self, hidden_units, embedding_size):
+        super(ADDJUST, self).__init__()
+        self.hidden_units = hidden_units
+        self.emb_size = embedding_size if not config.is_ComlexMask else 2 * embedding_size
+        self.layer = nn.Linear(hidden_units + self.emb_size, self.emb_size, bias=False)
+
+    def forward(self, input_hidden, prob_emb):
+        q, _ = _speaker_query(input_hidden.contiguous(), prob_emb.contiguous(), None,
+                              self.layer.weight.detach(), 0)
+        return q
+
+
+def top_k_mask(batch_pro, alpha, top_k):
+    """Host-side speaker selection, as in the reference (python loops over B; boundary glue)."""
+    size = batch_pro.size()
+    final = torch.zeros(size)
+    sort_result, sort_index = torch.sort(batch_pro.detach().cpu(), 1, True)
+    sort_index = sort_index[:, :top_k]
+    sort_result = torch.sum(sort_result > alpha, 1)
+    for line_idx in range(size[0]):
+        line_top_k = sort_index[line_idx][:int(sort_result[line_idx])]
+        for i in line_top_k.numpy():
+            final[line_idx, i] = 1
+    return final

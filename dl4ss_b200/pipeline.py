@@ -1,0 +1,95 @@
+"""Waveform -> separated waveforms, the whole hot path on the GPU.
+
+`Separator` strings the kernels in the order the reference's `eval_bss` does
+(TDAA_beta/main_run_sstune_EvalVer.py:407-507, cRM: TDAA_beta/main_run_sstune_cRM_EvalVer.py:498-570):
+    prepare_data (CPU librosa STFT)      -> K1  dl4ss_stft_feat          (one launch per batch)
+    MIX_SPEECH (cuDNN RNN + Linear+tanh) -> per layer: input projection GEMM + K3 persistent RNN
+    SPEECH_EMBEDDING + ADDJUST           -> dl4ss_speaker_query_fwd
+    expand().contiguous() + ATTENTION    -> K4  dl4ss_emb_attn_mask_fwd   (no [B,T,F,E] tensor)
+    mask*mix, bss_eval (CPU librosa istft, wav files) -> K6 dl4ss_mask_istft
+It takes the drop-in modules (dl4ss_b200.modules), so weights/checkpoints are the reference's.
+"""
+import torch
+
+from . import _lib
+from . import config
+from . import features
+from . import modules as M
+
+
+class Separator(object):
+    def __init__(self, mix_hidden_layer_3d, mix_speech_multiEmbedding, att_speech_layer, adjust_layer=None,
+                 n_fft=None, hop=None):
+        if att_speech_layer.mode != 'dot':
+            raise NotImplementedError("Separator fuses the 'dot' attention; run 'align' through the modules")
+        self.mix = mix_hidden_layer_3d
+        self.emb = mix_speech_multiEmbedding
+        self.att = att_speech_layer
+        self.adj = adjust_layer if (adjust_layer is not None and config.is_SelfTune) else None
+        self.n_fft = config.FRAME_LENGTH if n_fft is None else n_fft
+        self.hop = config.FRAME_SHIFT if hop is None else hop
+        self.complex_mask = bool(config.is_ComlexMask)
+        self.log_spectral = bool(config.IS_LOG_SPECTRAL)
+
+    # -- stages ---------------------------------------------------------------------------
+    def features(self, mix_wav):
+        return features.prepare_batch(mix_wav, self.n_fft, self.hop, self.log_spectral)
+
+    def queries(self, hidden, spk_idx):
+        idx = self.emb.index_tensor(spk_idx)
+        wadj = self.adj.layer.weight.detach() if self.adj is not None else None
+        q, err = M._speaker_query(hidden if wadj is not None else None, self.emb.layer.weight.detach(), idx,
+                                  wadj, 1)
+        return q, err
+
+    def masks(self, mix_feas, spk_idx, check_index=True):
+        """mix_feas [B,T,F], spk_idx int [B,S] -> masks [B,S,T,F] (cRM: decompressed [B,S,T,F,2])."""
+        B, T, F = mix_feas.shape
+        hidden = self.mix.encode(mix_feas)
+        q, err = self.queries(hidden, spk_idx)
+        lin = self.mix.Linear
+        E = lin.out_features // F
+        out = M.emb_attn_mask(hidden, lin.weight.detach(), lin.bias.detach(), q, F, E,
+                              complex_mask=self.complex_mask, decompress=True)
+        if check_index and int(err.item()):
+            raise IndexError('index out of range in self')
+        return out
+
+    def separate(self, mix_wav, spk_idx, return_all=False, check_index=True):
+        """mix_wav [B,L] CUDA f32/f64, spk_idx [B,S] -> separated wav [B,S,hop*(T-1)] float32."""
+        with torch.no_grad():
+            batch = self.features(mix_wav)
+            masks = self.masks(batch['mix_feas'], spk_idx, check_index)
+            wav = features.mask_istft(masks, batch['mix_mag'], self.hop, 'hann', self.n_fft)
+        if return_all:
+            batch['masks'] = masks
+            batch['wav'] = wav
+            return batch
+        return wav
+
+    __call__ = separate
+
+
+def mask_loss(masks, mix, target, complex_mask=None):
+    """The reference's training/eval objective from masks (K5).
+
+    real : MSE(mask*mix_feas, y) + 0.5*MSE(sum_s mask, 1)  (TDAA_beta/main_run_sstune_EvalVer.py:487-497)
+           mix = mix_feas [B,T,F], target [B,S,T,F]
+    cRM  : MSE(Re) + MSE(Im)                              (...cRM_EvalVer.py:545-568)
+           mix = mix_mag [B,T,F,2], target [B,S,T,F,2]
+    -> (loss, part0, part1) python floats... as 0-d CUDA float64 tensors (no host sync here)."""
+    lib = _lib.load()
+    cplx = (masks.dim() == 5) if complex_mask is None else complex_mask
+    B, S, T, F = masks.shape[:4]
+    acc = torch.zeros(2, device=masks.device, dtype=torch.float64)
+    rc = lib.dl4ss_mask_loss_fwd(_lib.ptr(masks, name='masks'), _lib.MASK_COMPLEX if cplx else _lib.MASK_REAL,
+                                 _lib.ptr(mix, name='mix'), _lib.ptr(target, name='target'), B, S, T * F,
+                                 _lib.ptr(acc, torch.float64), _lib.stream())
+    _lib.check(rc, 'dl4ss_mask_loss_fwd')
+    if cplx:
+        n = float(B * S * T * F)
+        l0, l1 = acc[0] / n, acc[1] / n
+        return l0 + l1, l0, l1
+    l0 = acc[0] / float(B * S * T * F)
+    l1 = acc[1] / float(B * T * F)
+    return l0 + 0.5 * l1, l0, l1

@@ -1,0 +1,150 @@
+/*
+ * dl4ss_b200 -- C ABI of the B200 (sm_100a) separation hot path.
+ *
+ * The reference (shincling/DL4SS) is pure Python: it has NO FFI / operator interface.  The
+ * boundary of its hot path is the set of Python calls listed per function below; this header
+ * is the C surface a binding for those calls uses (ctypes stub in INTEGRATION.md; the shipped
+ * binding is dl4ss_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DL4SS_E* code on failure;
+ *     dl4ss_last_error() returns a thread-local message.  Nothing throws across the ABI.
+ *   - all tensor arguments are caller-owned DEVICE pointers, contiguous, fp32 unless stated.
+ *     No function allocates device memory; scratch is passed in by the caller
+ *     (size from the matching *_workspace_bytes query).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - layouts are the reference's: features [B,T,F], complex spectra [B,T,F,2] (re,im) --
+ *     `convert2`, TDAA_beta/predata_fromList_cRM_123.py:37-41 --, masks [B,S,T,F] or
+ *     [B,S,T,F,2], waveforms [B,L] / [B,S,hop*(T-1)], RNN weights in torch.nn.LSTM/GRU
+ *     state-dict order (gate order LSTM i,f,g,o ; GRU r,z,n).
+ */
+#ifndef DL4SS_B200_H
+#define DL4SS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL4SS_OK            0
+#define DL4SS_EINVAL       -1   /* bad argument (shape, enum, null pointer)            */
+#define DL4SS_EUNSUPPORTED -2   /* valid request this build has no kernel for          */
+#define DL4SS_ECUDA        -3   /* CUDA runtime / launch error (message has the cause) */
+#define DL4SS_EWORKSPACE   -4   /* workspace too small                                  */
+
+#define DL4SS_FEAT_NONE 0       /* only the complex spectrum                            */
+#define DL4SS_FEAT_ABS  1       /* |X|          (TDAA_beta/predata_fromList.py:194)     */
+#define DL4SS_FEAT_LOG  2       /* log(|X|+eps) (TDAA_beta/predata_fromList.py:188-192) */
+
+#define DL4SS_WAV_F32 0
+#define DL4SS_WAV_F64 1         /* the reference's mix_wav is float64                   */
+
+#define DL4SS_MASK_NONE    0    /* spec is already per source [B,S,T,F,2]               */
+#define DL4SS_MASK_REAL    1    /* mask [B,S,T,F]   x mixture (a9)                      */
+#define DL4SS_MASK_COMPLEX 2    /* mask [B,S,T,F,2] x mixture, complex multiply (a10)   */
+
+#define DL4SS_CELL_LSTM 0
+#define DL4SS_CELL_GRU  1
+
+#define DL4SS_ACT_NONE    0
+#define DL4SS_ACT_TANH    1
+#define DL4SS_ACT_SIGMOID 2
+
+#define DL4SS_ATT_DOT      0    /* sigmoid(<emb,q>)          EvalVer.py:216-226          */
+#define DL4SS_ATT_DOT_CRM  1    /* K*tanh(<emb,q1|q2>) + decompress  cRM_EvalVer.py:260-271,512 */
+
+int         dl4ss_version(void);
+const char *dl4ss_last_error(void);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+uint64_t    dl4ss_launch_count(void);
+
+/* ---- K1: frame + window + FFT + |.|/log  ------------------------------------------------
+ * Replaces librosa.core.spectrum.stft(y, n_fft, hop) + np.abs / np.log / convert2 at
+ *   TDAA_beta/predata_fromList.py:166,179,188-200 ; Torch_multi/predata_multiAims.py:168,185,194-205 ;
+ *   TDAA_beta/predata_fromList_cRM_123.py:215-218,232-235,250-255.
+ * wav [B,L] (f32 or f64), centre=True reflect padding, T = 1 + L/hop, F = 1 + n_fft/2.
+ * window: n_fft fp32 taps on the device.  feat_out [B,T,F] (may be NULL when feat_mode NONE),
+ * cplx_out [B,T,F,2] (may be NULL).  n_fft must be 256 in this build.  conj!=0 conjugates the
+ * spectrum (librosa <= 0.5 flavour). */
+int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int n_fft, int hop,
+                    const float *window, int feat_mode, float eps, int conj,
+                    float *feat_out, float *cplx_out, void *stream);
+
+/* ---- K6: mask x mixture + iFFT + window + overlap-add + normalise -----------------------
+ * Replaces `pred = mask*mix_feas` ... `pred*exp(1j*angle(mix))` ... librosa.istft(spec.T, hop):
+ *   TDAA_beta/main_run_sstune_EvalVer.py:466-470,55-65 ; cRM: ...cRM_EvalVer.py:545-553,96-99.
+ * spec: mixture [B,T,F,2] (MASK_REAL / MASK_COMPLEX) or per-source [B,S,T,F,2] (MASK_NONE).
+ * wav_out [B,S,hop*(T-1)].  (mask*|X|)*exp(j*angle X) == mask*X, so the phase never
+ * materialises.  Imaginary parts of the DC / Nyquist bins are ignored, as in irfft. */
+int dl4ss_mask_istft(const float *mask, int mask_kind, const float *spec, int B, int S, int T,
+                     int n_fft, int hop, const float *window, float *wav_out, void *stream);
+
+/* ---- dense projection  C[M,N] = act(A[M,K] * W[N,K]^T + bias[N])  (fp32) ------------------
+ * The nn.Linear contractions on the path: RNN input projections and MIX_SPEECH.Linear
+ * (TDAA_beta/main_run_sstune_EvalVer.py:290,298-299) when the embedding is materialised,
+ * ADDJUST.layer (:369,375).  lda/ldw/ldc are row pitches in elements.  bias may be NULL. */
+int dl4ss_linear_fwd(const float *A, int lda, const float *W, int ldw, const float *bias,
+                     float *C, int ldc, int M, int N, int K, int act, void *stream);
+
+/* ---- K3: bidirectional recurrent layer (persistent kernel) -------------------------------
+ * Replaces one layer of nn.LSTM / nn.GRU(batch_first, bidirectional)
+ *   (TDAA_beta/main_run_sstune_EvalVer.py:282-289,293 ; ...cRM_EvalVer.py:345-351,356).
+ * xproj [B,T,2,G*H]: x*W_ih^T + b_ih (+ b_hh for every LSTM gate and the GRU r,z gates),
+ *   direction-major inside a frame, G = 4 (LSTM i,f,g,o) / 3 (GRU r,z,n).
+ * whh [2,G*H,H] ; bhn [2,H] (GRU b_hn; NULL for LSTM) ; y [B,T,2H] (fwd | reverse halves).
+ * Zero initial state.  workspace: dl4ss_rnn_workspace_bytes() bytes, zero-filled by callee.
+ * Optional training outputs (NULL in inference): gates_save [B,T,2,G*H] post-activation gates
+ * and cell_save [B,T,2,H] (LSTM c_t). */
+size_t dl4ss_rnn_workspace_bytes(int B, int T, int H, int cell);
+int dl4ss_rnn_layer_fwd(int cell, const float *xproj, const float *whh, const float *bhn,
+                        float *y, int B, int T, int H, float *gates_save, float *cell_save,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K4: Linear + tanh + speaker attention + mask, fused ---------------------------------
+ * Replaces MIX_SPEECH.Linear+tanh (EvalVer.py:298-301), the S-fold expand().contiguous()
+ * (:453-455), ATTENTION 'dot' (:216-226) and, for cRM, K*tanh + decompression
+ * (cRM_EvalVer.py:260-271,512), without materialising emb[B,T,F,E].
+ * h [B*T, K] ; W [F*E, K] ; bias [F*E] ; q [B,S,E] (DOT) or [B,S,2E] (DOT_CRM) ;
+ * mask_out [B,S,T,F] or [B,S,T,F,2].  crm_k / crm_c: K=10, C=0.1 in the reference
+ * (crm_c <= 0 skips the decompression and returns K*tanh).  workspace: at least one
+ * utterance of T*F*E floats; dl4ss_emb_attn_mask_workspace_bytes() returns the preferred size. */
+size_t dl4ss_emb_attn_mask_workspace_bytes(int B, int T, int F, int E);
+int dl4ss_emb_attn_mask_fwd(const float *h, const float *W, const float *bias, const float *q,
+                            int B, int T, int F, int E, int K, int S, int mode,
+                            float crm_k, float crm_c, float *mask_out,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- attention over a MATERIALISED embedding (module-level drop-in) ----------------------
+ * ATTENTION.forward(mix_hidden[N,T,F,E], query[N,E|2E]) (EvalVer.py:210-226).
+ * emb [Nb,TF,E]; emb_batch_stride = 0 shares one embedding across the S queries of an
+ * utterance (the reference's expand without the copy). */
+int dl4ss_attn_dot_fwd(const float *emb, long long emb_utt_stride, const float *q, int B, int S,
+                       int TF, int E, int mode, float crm_k, float crm_c, float *mask_out,
+                       void *stream);
+
+/* ---- speaker queries: embedding gather (+ ADDJUST self-tune) --------------------------------
+ * e = table[idx[b,s]] (idx NULL: `table` is e[B,S,EQ] itself) ;
+ * q[b,s,:] = residual*e + Wadj * [mean_t h[b,t,:] ; e]          (Wadj NULL: q = e, gather only)
+ *   SPEECH_EMBEDDING.forward TDAA_beta/main_run_sstune_EvalVer.py:357-361 (2E wide for cRM);
+ *   ADDJUST.forward + residual :371-377,445-446.
+ * h [B,T,C] ; table [num_spk,EQ] ; idx int64 [B,S] ; Wadj [EQ,C+EQ] ; q [B,S,EQ] ;
+ * hmean_out [B,C] optional (kept for backward) ; err_flag: device int set to 1 on an
+ * out-of-range speaker id (nn.Embedding raises; the caller checks it). */
+int dl4ss_speaker_query_fwd(const float *h, int B, int T, int C, const float *table, int num_spk,
+                            int EQ, const long long *idx, int S, const float *Wadj, int residual,
+                            float *q, float *hmean_out, int *err_flag, void *stream);
+
+/* ---- K5: mask x mixture + MSE losses ------------------------------------------------------
+ * real: loss_main = mean((mask*feas - y)^2), loss_sum = mean((sum_s mask - 1)^2)
+ *       (EvalVer.py:470,487-492) ; cRM: mean((Re)^2), mean((Im)^2) (cRM_EvalVer.py:545-568).
+ * partial sums are accumulated in double into loss_out[2] (caller zeroes it; the means are
+ * taken by the caller so shards of one global batch can be all-reduced first). */
+int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
+                        int B, int S, int TF, double *loss_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DL4SS_B200_H */

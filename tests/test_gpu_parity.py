@@ -1,0 +1,278 @@
+"""GPU parity tests: dl4ss_b200 (CUDA, through the C ABI) against the CPU oracle.
+
+Tolerances (north star: spectra/masks within 1e-4 relative in fp32, SDR within 0.01 dB):
+  * spectra, features, waveforms: max|a-b| <= 1e-4 * max|ref| per batch (relative to the peak);
+    measured values are ~1e-6.
+  * masks (values in (0,1)): max abs diff <= 1e-4 (== relative to the mask range), and the
+    element-wise relative error <= 1e-4 wherever the mask > 1e-2.
+  * SDR of separated outputs: |dSDR| <= 0.01 dB with the same bss_eval_sources restatement.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_err, build_pair
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _oracle_stft_batch(wav, hop, window='hann', conj=False):
+    from oracle import stft_ref as sr
+    return np.stack([sr.stft_ref(w, 256, hop, window, conj).T for w in wav])      # [B,T,F] c64
+
+
+@pytest.mark.parametrize('hop,L,B', [(128, 40000, 3), (64, 32000, 2), (128, 17040, 2), (128, 8191, 2),
+                                     (100, 5000, 1), (256, 4096, 2), (128, 129, 1)])
+def test_stft_matches_oracle(cuda, hop, L, B):
+    import dl4ss_b200 as d
+    rng = np.random.RandomState(L + hop)
+    wav = rng.standard_normal((B, L))
+    ref = _oracle_stft_batch(wav, hop)
+    for dtype in (torch.float64, torch.float32):
+        feat, cplx = d.stft_features(torch.from_numpy(wav).to(cuda, dtype), 256, hop, 'hann', 'abs')
+        assert tuple(feat.shape) == ref.shape and tuple(cplx.shape) == ref.shape + (2,)
+        got = torch.view_as_complex(cplx).cpu().numpy()
+        assert rel_err(got.real, ref.real) < TOL and rel_err(got.imag, ref.imag) < TOL
+        assert rel_err(feat.cpu().numpy(), np.abs(ref)) < TOL
+    # golden shape constants of the reference
+    assert ref.shape[1] == 1 + L // hop and ref.shape[2] == 129
+
+
+def test_stft_golden_shapes(cuda):
+    import dl4ss_b200 as d
+    f, _ = d.stft_features(torch.zeros(5, 17040, device=cuda), 256, 128)     # Torch_multi/predata_multiAims.py:58
+    assert tuple(f.shape) == (5, 134, 129)
+    f, c = d.stft_features(torch.zeros(1, 40000, device=cuda), 256, 128)     # T=313 pinned by Linear(36480,1)
+    assert tuple(f.shape) == (1, 313, 129)
+    w = d.mask_istft(None, c.view(1, 1, 313, 129, 2), 128)
+    assert tuple(w.shape) == (1, 1, 39936)                                   # EvalVer.py:49
+
+
+def test_stft_log_sine_and_conj(cuda):
+    import dl4ss_b200 as d
+    from oracle import stft_ref as sr
+    rng = np.random.RandomState(7)
+    wav = rng.standard_normal((2, 16000))
+    wav[1, 4000:9000] = 0.0                       # digital silence -> log(eps) floor
+    ref = np.stack([sr.features_ref(w, 256, 128, log_spectral=True, window='sine')['mix_feas'] for w in wav])
+    feat, _ = d.stft_features(torch.from_numpy(wav).to(cuda), 256, 128, 'sine', 'log', want_complex=False)
+    got = feat.cpu().numpy()
+    loud = ref > -10.0                             # log magnifies relative error of tiny magnitudes
+    assert np.abs(got - ref)[loud].max() < 1e-3
+    silent = ref < -30.0
+    assert silent.any() and np.abs(got[silent] - np.log(np.spacing(1))) .max() < 1e-3
+    refc = _oracle_stft_batch(wav, 128, conj=True)
+    _, c = d.stft_features(torch.from_numpy(wav).to(cuda), 256, 128, 'hann', None, conj=True)
+    assert rel_err(torch.view_as_complex(c).cpu().numpy().imag, refc.imag) < TOL
+    # list-of-taps window like config.WINDOWS
+    taps = d.config.sine_window(256)
+    f2, _ = d.stft_features(torch.from_numpy(wav).to(cuda), 256, 128, taps, 'log', want_complex=False)
+    assert torch.equal(f2, feat)
+
+
+@pytest.mark.parametrize('hop,T,B,S', [(128, 313, 2, 2), (128, 134, 1, 3), (64, 201, 2, 2), (128, 2, 1, 1),
+                                       (256, 17, 1, 2), (100, 51, 1, 5), (128, 40, 1, 20)])
+def test_istft_matches_oracle(cuda, hop, T, B, S):
+    import dl4ss_b200 as d
+    from oracle import stft_ref as sr
+    rng = np.random.RandomState(T * 7 + S)
+    spec = (rng.standard_normal((B, S, T, 129)) + 1j * rng.standard_normal((B, S, T, 129))).astype(np.complex64)
+    ref = np.array([[sr.istft_ref(spec[b, s].T, hop) for s in range(S)] for b in range(B)])
+    st = torch.view_as_real(torch.from_numpy(spec)).to(cuda).contiguous()
+    got = d.mask_istft(None, st, hop).cpu().numpy()
+    assert got.shape == ref.shape == (B, S, hop * (T - 1))
+    assert rel_err(got, ref) < TOL
+
+
+def test_mask_istft_real_and_complex(cuda):
+    import dl4ss_b200 as d
+    from oracle import stft_ref as sr
+    rng = np.random.RandomState(3)
+    B, S, T, hop = 2, 3, 150, 128
+    X = (rng.standard_normal((B, T, 129)) + 1j * rng.standard_normal((B, T, 129))).astype(np.complex64)
+    m = rng.uniform(0, 1, (B, S, T, 129)).astype(np.float32)
+    # reference form: (mask*|X|) * exp(j*angle(X))   (EvalVer.py:55-63)
+    ref = np.array([[sr.istft_ref(((m[b, s] * np.abs(X[b])) * np.exp(1j * np.angle(X[b]))).T, hop)
+                     for s in range(S)] for b in range(B)])
+    Xt = torch.view_as_real(torch.from_numpy(X)).to(cuda).contiguous()
+    got = d.mask_istft(torch.from_numpy(m).to(cuda), Xt, hop).cpu().numpy()
+    assert rel_err(got, ref) < TOL
+    mc = (rng.standard_normal((B, S, T, 129, 2)) * 2).astype(np.float32)
+    pr = mc[..., 0] * X.real[:, None] - mc[..., 1] * X.imag[:, None]      # cRM_EvalVer.py:550-553
+    pi = mc[..., 0] * X.imag[:, None] + mc[..., 1] * X.real[:, None]
+    refc = np.array([[sr.istft_ref((pr[b, s] + 1j * pi[b, s]).T, hop) for s in range(S)] for b in range(B)])
+    gotc = d.mask_istft(torch.from_numpy(mc).to(cuda), Xt, hop).cpu().numpy()
+    assert rel_err(gotc, refc) < TOL
+
+
+def test_stft_istft_roundtrip_full_size(cuda):
+    """Size-independent property at BASELINE batch size: iSTFT(STFT(x)) == x away from nothing."""
+    import dl4ss_b200 as d
+    B, L = 256, 40000
+    g = torch.Generator(device='cuda').manual_seed(1)
+    wav = torch.randn(B, L, device=cuda, generator=g)
+    _, c = d.stft_features(wav, 256, 128, 'hann', None)
+    back = d.mask_istft(None, c.view(B, 1, 313, 129, 2), 128)
+    assert tuple(back.shape) == (B, 1, 39936)
+    err = (back[:, 0] - wav[:, :39936]).abs().max().item()
+    assert err < 1e-4 * wav.abs().max().item()
+    ones = torch.ones(B, 1, 313, 129, device=cuda)
+    back2 = d.mask_istft(ones, c, 128)
+    assert torch.equal(back, back2)          # identity mask == no mask, bit for bit
+    # linearity in the mask
+    half = d.mask_istft(0.5 * ones, c, 128)
+    assert (half - 0.5 * back).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize('M,N,K,act', [(300, 2400, 129, 'none'), (257, 6450, 600, 'tanh'), (5, 50, 650, 'none'),
+                                        (1000, 100, 64, 'sigmoid'), (128, 128, 16, 'none'), (1, 1, 1, 'none')])
+def test_linear_matches_torch(cuda, M, N, K, act):
+    import dl4ss_b200 as d
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K)
+    w = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    ref = x.double() @ w.double().t() + b.double()
+    ref = {'none': ref, 'tanh': torch.tanh(ref), 'sigmoid': torch.sigmoid(ref)}[act]
+    got = d.linear_fwd(x.to(cuda), w.to(cuda), b.to(cuda), act).cpu()
+    assert (got.double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize('cell,layers,B,T', [('lstm', 2, 3, 37), ('gru', 2, 5, 29), ('lstm', 4, 40, 25),
+                                              ('gru', 2, 70, 21), ('lstm', 1, 9, 5)])
+def test_rnn_matches_torch(cuda, cell, layers, B, T):
+    """All three tile configurations (B<=8, <=32, >32) and both cells vs nn.LSTM/nn.GRU on CPU."""
+    import dl4ss_b200 as d
+    ref, ours = build_pair(cell, layers, 129, T, False)
+    torch.manual_seed(5)
+    x = torch.rand(B, T, 129) * 2
+    with torch.no_grad():
+        y_ref, _ = ref['mix'].layer(x)
+        y = ours['mix'].encode(x.to(cuda)).cpu()
+    assert tuple(y.shape) == (B, T, 600)
+    assert (y - y_ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize('cell,layers,cplx,S,B,T', [('lstm', 2, False, 2, 3, 40), ('gru', 2, True, 3, 2, 33),
+                                                     ('lstm', 4, False, 2, 2, 60)])
+def test_masks_match_oracle(cuda, cell, layers, cplx, S, B, T):
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    ref, ours = build_pair(cell, layers, 129, T, cplx)
+    torch.manual_seed(11)
+    feas = torch.rand(B, T, 129) * 3
+    mag = torch.randn(B, T, 129, 2)
+    idx = np.sort(np.random.RandomState(2).choice(101, (B, S)), axis=1)
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, idx, mag)
+    sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    m = sep.masks(feas.to(cuda), idx).cpu()
+    rm = r['masks']
+    assert m.shape == rm.shape
+    if not cplx:
+        assert (m - rm).abs().max().item() < TOL
+        big = rm > 1e-2
+        assert ((m - rm).abs() / rm)[big].max().item() < TOL
+    else:
+        assert ((m - rm).abs() / (rm.abs() + 1.0)).max().item() < TOL
+    # module-level drop-in (the reference glue, verbatim shape calls) gives the same masks
+    E = 50
+    with torch.no_grad():
+        hid, tmp = ours['mix'](feas.to(cuda))
+        embs = ours['emb'](None, idx)
+        embs = ours['adj'](tmp, embs) + embs
+        h5 = hid.view(B, 1, T, 129, E).expand(B, S, T, 129, E).contiguous().view(-1, T, 129, E)
+        att = ours['att'](h5, embs.view(-1, 2 * E if cplx else E))
+        if cplx:
+            att = d.crm_decompress(att.view(B, S, T, 129, 2))
+        else:
+            att = att.view(B, S, T, 129)
+    assert (att.cpu() - m).abs().max().item() < 1e-5 * (1.0 + m.abs().max().item())
+    # un-fused module path (materialised embedding) agrees as well
+    ours['mix'].fused = False
+    with torch.no_grad():
+        hid2, _ = ours['mix'](feas.to(cuda))
+        assert tuple(hid2.shape) == (B, T, 129, E)
+        ref_emb, _ = ref['mix'](feas)
+        assert (hid2.cpu() - ref_emb).abs().max().item() < 2e-5
+        h5 = hid2.view(B, 1, T, 129, E).expand(B, S, T, 129, E).contiguous().view(-1, T, 129, E)
+        att2 = ours['att'](h5, embs.view(-1, 2 * E if cplx else E))
+    att2 = d.crm_decompress(att2.view(B, S, T, 129, 2)) if cplx else att2.view(B, S, T, 129)
+    assert (att2.cpu() - m).abs().max().item() < 1e-5 * (1.0 + m.abs().max().item())
+
+
+def test_align_attention_matches_oracle(cuda):
+    import dl4ss_b200 as d
+    ref, ours = build_pair('lstm', 1, 129, 12, False, mode='align')
+    torch.manual_seed(3)
+    emb = torch.tanh(torch.randn(4, 12, 129, 50))
+    q = torch.randn(4, 50)
+    with torch.no_grad():
+        r = ref['att'](emb, q)
+        g = ours['att'](emb.to(cuda), q.to(cuda)).cpu()
+    assert (g - r).abs().max().item() < 2e-5
+
+
+def test_embedding_index_error(cuda):
+    import dl4ss_b200 as d
+    _, ours = build_pair('lstm', 1, 129, 4, False)
+    with pytest.raises(IndexError):
+        ours['emb'](None, [[0, 101]])
+
+
+def test_end_to_end_separation_sdr(cuda):
+    """waveform -> waveforms: masks, spectra, waveforms within 1e-4 and SDR within 0.01 dB."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr, stft_ref as sr, synth, bss_eval_ref as be
+    B, L, S, hop = 3, 16000, 2, 128
+    batch = synth.make_batch(B, L, S, seed=1)
+    T = 1 + L // hop
+    ref, ours = build_pair('lstm', 2, 129, T, False)
+    feats = [sr.features_ref(w, 256, hop) for w in batch['mix_wav']]
+    feas = torch.from_numpy(np.stack([f['mix_feas'] for f in feats]))
+    phase = np.stack([f['mix_phase'] for f in feats])
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, batch['spk_idx'])
+    wav_ref = mr.reconstruct_ref(r, phase, hop)
+    sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    out = sep.separate(torch.from_numpy(batch['mix_wav']).to(cuda), batch['spk_idx'], return_all=True)
+    assert rel_err(out['mix_feas'].cpu().numpy(), feas.numpy()) < TOL
+    assert (out['masks'].cpu() - r['masks']).abs().max().item() < TOL
+    wav = out['wav'].cpu().numpy()
+    assert wav.shape == wav_ref.shape
+    assert rel_err(wav, wav_ref) < TOL
+    n = wav.shape[-1]
+    for b in range(B):
+        sdr_ref = be.bss_eval_sources(batch['sources'][b][:, :n], wav_ref[b])[0]
+        sdr_got = be.bss_eval_sources(batch['sources'][b][:, :n], wav[b])[0]
+        assert np.abs(sdr_ref - sdr_got).max() < 0.01
+    # loss (K5) against the oracle's MSELoss form
+    y = torch.from_numpy(np.stack([[np.abs(sr.stft_ref(s, 256, hop)).T for s in srcs] for srcs in batch['sources']]))
+    lref = mr.loss_ref(ref['cfg'], r, y.float())
+    l, l0, l1 = d.mask_loss(out['masks'], out['mix_feas'], y.float().to(cuda).contiguous())
+    assert abs(l.item() - lref[0].item()) < 1e-5 * abs(lref[0].item()) + 1e-7
+    assert abs(l0.item() - lref[1].item()) < 1e-5 * abs(lref[1].item()) + 1e-7
+
+
+def test_end_to_end_crm(cuda):
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr, stft_ref as sr, synth
+    B, L, S, hop = 2, 12800, 3, 128
+    batch = synth.make_batch(B, L, S, seed=4)
+    T = 1 + L // hop
+    ref, ours = build_pair('gru', 2, 129, T, True)
+    feats = [sr.features_ref(w, 256, hop) for w in batch['mix_wav']]
+    feas = torch.from_numpy(np.stack([f['mix_feas'] for f in feats]))
+    mag = torch.from_numpy(np.stack([f['mix_mag'] for f in feats]))
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, batch['spk_idx'], mag)
+    wav_ref = mr.reconstruct_ref(r, None, hop, complex_mask=True)
+    sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    out = sep.separate(torch.from_numpy(batch['mix_wav']).to(cuda), batch['spk_idx'], return_all=True)
+    assert rel_err(out['wav'].cpu().numpy(), wav_ref) < TOL
+    y = torch.randn(B, S, T, 129, 2)
+    lref = mr.loss_ref(ref['cfg'], r, y)
+    l, _, _ = d.mask_loss(out['masks'], out['mix_mag'], y.to(cuda))
+    assert abs(l.item() - lref[0].item()) < 1e-4 * abs(lref[0].item())
