@@ -11,7 +11,8 @@ from . import config  # noqa: F401
 from ._lib import load as load_library, launch_count  # noqa: F401
 from .features import stft_features, mask_istft, prepare_batch, window_tensor  # noqa: F401
 from .modules import (MIX_SPEECH, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
-                      DeferredEmbedding, linear_fwd, rnn_forward, emb_attn_mask, crm_decompress)
+                      DeferredEmbedding, linear_fwd, linear_tc, split_bf16, weight_planes, rnn_forward,
+                      emb_attn_mask, crm_decompress)
 from .pipeline import Separator, mask_loss  # noqa: F401
 
 __version__ = '0.1.0'

@@ -36,3 +36,9 @@ def sine_window(win_size=None):
     """The window init_config() installs for the log-spectral mode (Torch_multi/config.py:238-240)."""
     n = FRAME_LENGTH if win_size is None else win_size
     return [np.sin(x_i * np.pi / n) for x_i in range(n)]
+
+# Not in the reference: numeric mode of the dense projections on the GPU.
+#   'bf16x3' tcgen05 tensor cores, operands split into two bf16 planes, three MMAs per product,
+#            fp32 accumulation: masks within ~2e-6 of fp32 (the default);
+#   'fp32'   CUDA-core FMA, bit-close to an SGEMM (the yard-stick the tests compare 'bf16x3' with).
+GEMM_PRECISION = 'bf16x3'

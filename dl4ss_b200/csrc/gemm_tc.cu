@@ -1,0 +1,456 @@
+// Tensor-core projections for sm_100a: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation in
+// TMEM), operands fed by TMA into 128B-swizzled shared memory, warp-specialised persistent CTAs.
+//
+// fp32 parity on bf16 tensor cores ("bf16x3"): every fp32 operand is pre-split into two bf16 planes
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 significant bits together) and each k-block
+// issues three MMAs  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi  into the same fp32 accumulator.  Measured
+// against fp64 on the full model the masks move by ~1e-6 (single-pass bf16: 9e-4, tf32: 1.2e-4 --
+// both outside the 1e-4 parity bar).
+//
+//   dl4ss_split_bf16              fp32 [R,K] -> bf16 planes [2][R][Kp], Kp = K rounded up to 64
+//   dl4ss_linear_tc_fwd           C = A*W^T + bias                       (RNN input projections)
+//   dl4ss_emb_attn_mask_tc_fwd    K4: (h*W^T + b) -> tanh -> <.,q_s> over E -> sigmoid | cRM,
+//                                 evaluated in the epilogue straight out of TMEM: the [B,T,F,E]
+//                                 embedding (8 MB/utterance) never exists anywhere.
+//
+// Tile 128 x 256 x 64, 2 smem stages x (A_hi,A_lo,B_hi,B_lo) = 192 KB, 2 TMEM accumulator stages x
+// 256 columns; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace dl4ss {
+
+constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 2;
+constexpr int TA_BYTES = TBM * TBK * 2;                       // 16 KB
+constexpr int TB_BYTES = TBN * TBK * 2;                       // 32 KB
+constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
+constexpr int TC_THREADS = 192;
+constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------ split
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ x, int ld, long long R, int K, int Kp, __nv_bfloat16 *__restrict__ planes) {
+    const int chunks = Kp >> 3;
+    const long long total = R * chunks;
+    __nv_bfloat16 *hi = planes, *lo = planes + (size_t)R * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / chunks;
+        const int k0 = (int)(i - r * chunks) * 8;
+        const float *src = x + (size_t)r * ld + k0;
+        float v[8];
+        if (k0 + 8 <= K && (((uintptr_t)src) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4 *>(src);
+            const float4 b = *reinterpret_cast<const float4 *>(src + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (k0 + j < K) ? src[j] : 0.f;
+        }
+        __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = __float2bfloat16_rn(v[j]);
+            l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+        }
+        *reinterpret_cast<uint4 *>(hi + (size_t)r * Kp + k0) = *reinterpret_cast<const uint4 *>(h);
+        *reinterpret_cast<uint4 *>(lo + (size_t)r * Kp + k0) = *reinterpret_cast<const uint4 *>(l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+struct EpiPlain {
+    float *C;
+    const float *bias;
+    int ldc;
+};
+struct EpiAttn {
+    const float *bias;   // [F*E]
+    const float *q;      // [B,S,EQ]
+    float *out;          // [B,S,T,F] or [B,S,T,F,2]
+    int T, F, S, crm;    // crm: 0 sigmoid masks, 1 cRM pairs
+    float crm_k, crm_c;
+};
+
+constexpr int ATT_E = 50;                       // embedding width the fused epilogue is built for
+constexpr int ATT_EP = 64;                      // MMA columns per frequency bin (TMA zero-fills rows 50..63)
+constexpr int ATT_BINS = TBN / ATT_EP;          // 4 frequency bins per N tile
+constexpr int ATT_SMAX = 4;                     // speakers per utterance handled in registers
+
+template <typename Epi> struct EpiTraits;
+template <> struct EpiTraits<EpiPlain> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; };
+template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS; static constexpr bool BINNED = true; };
+
+__device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float crm_c) {
+    float m = crm_k * tanhf(energy);
+    if (crm_c <= 0.f) return m;
+    return (-1.0f / crm_c) * logf((crm_k - m) / (crm_k + m));
+}
+
+// one accumulator row (this thread's TMEM lane) -> global
+__device__ __forceinline__ void epilogue_row(const EpiPlain &e, uint32_t taddr, int m, int n0, int M, int N) {
+    float *crow = e.C + (size_t)m * e.ldc;
+    const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < TBN / 16; ++c) {
+        float v[16];
+        tmem_ld16(taddr + c * 16, v);          // warp-collective: executed by every lane
+        if (m >= M) continue;
+        const int n = n0 + c * 16;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            if (vec && n + j + 3 < N) {
+                float4 o;
+                o.x = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+                o.y = v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f);
+                o.z = v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f);
+                o.w = v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f);
+                *reinterpret_cast<float4 *>(crow + n + j) = o;
+            } else {
+#pragma unroll
+                for (int jj = j; jj < j + 4; ++jj)
+                    if (n + jj < N) crow[n + jj] = v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f);
+            }
+        }
+    }
+}
+
+// n0 = first frequency bin of the tile; bin j of the tile sits in accumulator columns [64j, 64j+50)
+__device__ __forceinline__ void epilogue_row(const EpiAttn &e, uint32_t taddr, int m, int n0, int M, int N) {
+    const int EQ = e.crm ? 2 * ATT_E : ATT_E;
+    const bool valid = m < M;
+    const int mm = valid ? m : 0;
+    const int b = mm / e.T, t = mm - b * e.T;
+    const float *qb = e.q + (size_t)b * e.S * EQ;
+#pragma unroll 1
+    for (int bin = 0; bin < ATT_BINS; ++bin) {
+        const int f = n0 + bin;
+        const bool fvalid = f < e.F;                      // warp-uniform
+        const float *bias = e.bias + (size_t)(fvalid ? f : 0) * ATT_E;
+        float en[2 * ATT_SMAX];
+#pragma unroll
+        for (int s = 0; s < 2 * ATT_SMAX; ++s) en[s] = 0.f;
+#pragma unroll
+        for (int c = 0; c < ATT_EP / 16; ++c) {
+            float v[16];
+            tmem_ld16(taddr + bin * ATT_EP + c * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int ee = c * 16 + j;                // compile time
+                if (ee >= ATT_E) continue;
+                const float x = tanh_f(v[j] + __ldg(bias + ee));
+#pragma unroll
+                for (int s = 0; s < ATT_SMAX; ++s) {
+                    if (s < e.S) {
+                        en[2 * s] = fmaf(x, __ldg(qb + s * EQ + ee), en[2 * s]);
+                        if (e.crm) en[2 * s + 1] = fmaf(x, __ldg(qb + s * EQ + ATT_E + ee), en[2 * s + 1]);
+                    }
+                }
+            }
+        }
+        if (valid && fvalid) {
+#pragma unroll
+            for (int s = 0; s < ATT_SMAX; ++s) {
+                if (s < e.S) {
+                    const size_t o = (((size_t)b * e.S + s) * e.T + t) * e.F + f;
+                    if (!e.crm) {
+                        e.out[o] = sigmoid_f(en[2 * s]);
+                    } else {
+                        reinterpret_cast<float2 *>(e.out)[o] =
+                            make_float2(crm_value_tc(en[2 * s], e.crm_k, e.crm_c),
+                                        crm_value_tc(en[2 * s + 1], e.crm_k, e.crm_c));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <typename Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   int M, int N, int kblocks, int m_tiles, int n_tiles, const Epi epi) {
+    constexpr int NSTEP = EpiTraits<Epi>::NSTEP;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)TSTAGES * TSTAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + TSTAGES, *tfull = bars + 2 * TSTAGES, *tempty = bars + 2 * TSTAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TSTAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char *st = tiles + (size_t)stage * TSTAGE_BYTES;
+                    mbar_expect_tx(&full[stage], TSTAGE_BYTES);
+                    tma_load_3d(st, &tmap_a, &full[stage], kb * TBK, m0, 0);
+                    tma_load_3d(st + TA_BYTES, &tmap_a, &full[stage], kb * TBK, m0, 1);
+                    if (EpiTraits<Epi>::BINNED) {      // W viewed [plane][F][E][K]: 4 bins x 64 (50 real) rows
+                        tma_load_4d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, 0, n0, 0);
+                        tma_load_4d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, 0, n0, 1);
+                    } else {
+                        tma_load_3d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
+                        tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
+                    }
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * TBN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * TSTAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TA_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * TA_BYTES), b_lo = umma_desc_sw128(sa + 2 * TA_BYTES + TB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; ++k) {        // +32 B per 16-element k step (>>4 = 2)
+                        umma_bf16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+                        umma_bf16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TBN;
+            epilogue_row(epi, taddr, m0 + quarter * 32 + lane, n0, M, N);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// planes: bf16 [2][R][Kp]; box = 64 (K) x rows x 1 plane, 128B swizzle, OOB rows zero-filled
+static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int Kp, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)R, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(planes), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) R=%lld Kp=%d", (int)r, R, Kp); return DL4SS_ECUDA; }
+    return DL4SS_OK;
+}
+
+// W planes bf16 [2][F*E][Kp] viewed as [2][F][E][Kp]; box = 64 (K) x 64 (E, rows >= E zero-filled) x 4 bins
+static int make_binned_map(CUtensorMap *map, const void *planes, int F, int E, int Kp) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)E, (cuuint64_t)F, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)E * Kp * 2, (cuuint64_t)F * E * Kp * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)ATT_EP, (cuuint32_t)ATT_BINS, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(planes), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (binned) failed (%d)", (int)r); return DL4SS_ECUDA; }
+    return DL4SS_OK;
+}
+
+template <typename Epi>
+static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, int K, int n_tiles, const Epi &epi,
+                     cudaStream_t st, int binned_F = 0) {
+    const int Kp = (K + TBK - 1) / TBK * TBK;
+    CUtensorMap ma, mb;
+    int rc = make_plane_map(&ma, a_planes, M, Kp, TBM);
+    if (rc) return rc;
+    rc = binned_F ? make_binned_map(&mb, w_planes, binned_F, ATT_E, Kp) : make_plane_map(&mb, w_planes, N, Kp, TBN);
+    if (rc) return rc;
+    const int m_tiles = cdiv(M, TBM);
+    const long long total = (long long)m_tiles * n_tiles;
+    int grid = sm_count();
+    if (total < grid) grid = (int)total;
+    auto kern = gemm_bf16x3_kernel<Epi>;
+    DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, epi);
+    DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel");
+    return DL4SS_OK;
+}
+
+}  // namespace dl4ss
+
+using namespace dl4ss;
+
+extern "C" size_t dl4ss_split_bf16_bytes(long long R, int K) {
+    if (R <= 0 || K <= 0) return 0;
+    const size_t Kp = (size_t)(K + TBK - 1) / TBK * TBK;
+    return 2 * (size_t)R * Kp * sizeof(__nv_bfloat16);
+}
+
+extern "C" int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, void *stream) {
+    DL4SS_CHECK_ARG(x && planes, "split_bf16: null operand");
+    DL4SS_CHECK_ARG(R >= 0 && K >= 1 && ld >= K, "split_bf16: bad R/K/ld %lld/%d/%d", R, K, ld);
+    DL4SS_CHECK_ARG((((uintptr_t)planes) & 15) == 0, "split_bf16: planes must be 16-byte aligned");
+    if (R == 0) return DL4SS_OK;
+    const int Kp = (K + TBK - 1) / TBK * TBK;
+    const long long total = R * (Kp / 8);
+    long long blocks = cdivll(total, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, R, K, Kp, (__nv_bfloat16 *)planes);
+    DL4SS_LAUNCH_CHECK("split_bf16_kernel");
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C, int ldc,
+                                   int M, int N, int K, void *stream) {
+    DL4SS_CHECK_ARG(a_planes && w_planes && C, "linear_tc_fwd: null operand");
+    DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "linear_tc_fwd: bad M/N/K/ldc %d/%d/%d/%d", M, N, K, ldc);
+    if (M == 0) return DL4SS_OK;
+    EpiPlain e{C, bias, ldc};
+    return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), e, (cudaStream_t)stream);
+}
+
+extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
+                                          const float *q, int B, int T, int F, int E, int K, int S, int mode,
+                                          float crm_k, float crm_c, float *mask_out, void *stream) {
+    DL4SS_CHECK_ARG(h_planes && w_planes && bias && q && mask_out, "emb_attn_mask_tc_fwd: null operand");
+    DL4SS_CHECK_ARG(B >= 0 && T >= 1 && F >= 1 && K >= 1 && S >= 1, "emb_attn_mask_tc_fwd: bad shape");
+    DL4SS_CHECK_ARG(mode == DL4SS_ATT_DOT || mode == DL4SS_ATT_DOT_CRM, "emb_attn_mask_tc_fwd: bad mode %d", mode);
+    if (E != ATT_E || S > ATT_SMAX) {
+        set_error("emb_attn_mask_tc_fwd: fused epilogue is built for E=%d, S<=%d (got E=%d S=%d)", ATT_E, ATT_SMAX, E, S);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0) return DL4SS_OK;
+    DL4SS_CHECK_ARG((long long)B * T < (1ll << 31), "emb_attn_mask_tc_fwd: B*T too large");
+    EpiAttn e{bias, q, mask_out, T, F, S, mode == DL4SS_ATT_DOT_CRM ? 1 : 0, crm_k, crm_c};
+    return launch_tc(h_planes, w_planes, B * T, F * E, K, cdiv(F, ATT_BINS), e, (cudaStream_t)stream, F);
+}

@@ -41,6 +41,43 @@ def linear_fwd(x2d, weight, bias=None, act='none', out=None):
     return out
 
 
+def split_bf16(x2d):
+    """fp32 [R,K] -> bf16 hi/lo planes [2,R,Kp] (Kp = K rounded up to 64) for the tcgen05 GEMMs."""
+    lib = _lib.load()
+    R, K = x2d.shape
+    Kp = (K + 63) // 64 * 64
+    planes = torch.empty(2, R, Kp, device=x2d.device, dtype=torch.bfloat16)
+    rc = lib.dl4ss_split_bf16(_lib.ptr(x2d, name='x'), x2d.stride(0), R, K, _lib.ptr(planes, torch.bfloat16),
+                              _lib.stream())
+    _lib.check(rc, 'dl4ss_split_bf16')
+    return planes
+
+
+def weight_planes(w):
+    """bf16 planes of a weight matrix, cached ON the tensor object and re-split only when the
+    parameter is modified in place (optimizer step, load_state_dict) or moved."""
+    ent = getattr(w, '_dl4ss_planes', None)
+    if ent is None or ent[0] != w._version or ent[1] != w.data_ptr():
+        ent = (w._version, w.data_ptr(), split_bf16(w.detach().contiguous()))
+        w._dl4ss_planes = ent
+    return ent[2]
+
+
+def linear_tc(a_planes, w_planes, bias, M, N, K, out=None):
+    """a[M,K] @ w[N,K]^T + bias from pre-split planes on tcgen05 (bf16x3, fp32 accumulate)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(M, N, device=a_planes.device, dtype=torch.float32)
+    rc = lib.dl4ss_linear_tc_fwd(_lib.ptr(a_planes, torch.bfloat16), _lib.ptr(w_planes, torch.bfloat16),
+                                 _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0), M, N, K, _lib.stream())
+    _lib.check(rc, 'dl4ss_linear_tc_fwd')
+    return out
+
+
+def use_tensor_cores():
+    return config.GEMM_PRECISION == 'bf16x3'
+
+
 class _PackedRNN(object):
     """Per-layer operands of the recurrent kernel, rebuilt only when a parameter changes."""
 
@@ -100,7 +137,11 @@ def rnn_forward(packed, x, save=None):
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
     for lw in packed.get():
-        linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
+        if use_tensor_cores():
+            x2d = inp.view(B * T, -1)
+            linear_tc(split_bf16(x2d), weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
+        else:
+            linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
         y = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
         gates = cells = None
         if save is not None:
@@ -125,6 +166,15 @@ def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=T
     dev = h.device
     mode = _lib.ATT_DOT_CRM if complex_mask else _lib.ATT_DOT
     out = torch.empty((B, S, T, F, 2) if complex_mask else (B, S, T, F), device=dev, dtype=torch.float32)
+    query = query.contiguous()
+    if use_tensor_cores() and E == 50 and S <= 4:
+        rc = lib.dl4ss_emb_attn_mask_tc_fwd(_lib.ptr(split_bf16(h.view(B * T, K)), torch.bfloat16),
+                                            _lib.ptr(weight_planes(weight), torch.bfloat16),
+                                            _lib.ptr(bias, name='bias'), _lib.ptr(query, name='query'),
+                                            B, T, F, E, K, S, mode, float(config.cRM_k),
+                                            float(config.cRM_C if decompress else 0.0), _lib.ptr(out), _lib.stream())
+        _lib.check(rc, 'dl4ss_emb_attn_mask_tc_fwd')
+        return out
     ws_bytes = int(lib.dl4ss_emb_attn_mask_workspace_bytes(B, T, F, E))
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     rc = lib.dl4ss_emb_attn_mask_fwd(_lib.ptr(h, name='h'), _lib.ptr(weight, name='weight'),
@@ -236,7 +286,7 @@ class MIX_SPEECH(nn.Module):
         xx = self.encode(x)
         E = self.Linear.out_features // self.input_fre
         if self.fused:
-            out = DeferredEmbedding(xx, self.Linear.weight.detach(), self.Linear.bias.detach(), F, E)
+            out = DeferredEmbedding(xx, self.Linear.weight, self.Linear.bias, F, E)
         else:
             out = linear_fwd(xx.view(B * T, -1), self.Linear.weight.detach(), self.Linear.bias.detach(),
                              'tanh').view(B, T, F, E)

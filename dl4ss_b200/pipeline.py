@@ -49,7 +49,7 @@ class Separator(object):
         q, err = self.queries(hidden, spk_idx)
         lin = self.mix.Linear
         E = lin.out_features // F
-        out = M.emb_attn_mask(hidden, lin.weight.detach(), lin.bias.detach(), q, F, E,
+        out = M.emb_attn_mask(hidden, lin.weight, lin.bias, q, F, E,
                               complex_mask=self.complex_mask, decompress=True)
         if check_index and int(err.item()):
             raise IndexError('index out of range in self')

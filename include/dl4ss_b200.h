@@ -116,6 +116,21 @@ int dl4ss_emb_attn_mask_fwd(const float *h, const float *W, const float *bias, c
                             float crm_k, float crm_c, float *mask_out,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- tensor-core projections (tcgen05, bf16x3 split: fp32-grade results) ------------------
+ * Same contractions as dl4ss_linear_fwd / dl4ss_emb_attn_mask_fwd on the 5th-gen tensor cores.
+ * Operands are first split into two bf16 planes (x = hi + lo) laid out [2][R][Kp],
+ * Kp = K rounded up to 64, zero padded; three MMAs per k-block (hi*hi + hi*lo + lo*hi) accumulate
+ * in fp32 TMEM.  `planes` buffers are caller-owned, 16-byte aligned, dl4ss_split_bf16_bytes()
+ * bytes.  The fused K4 epilogue is built for E = 50 (every reference config) and S <= 4;
+ * anything else returns DL4SS_EUNSUPPORTED and the caller uses dl4ss_emb_attn_mask_fwd. */
+size_t dl4ss_split_bf16_bytes(long long R, int K);
+int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, void *stream);
+int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
+                        int ldc, int M, int N, int K, void *stream);
+int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
+                               const float *q, int B, int T, int F, int E, int K, int S, int mode,
+                               float crm_k, float crm_c, float *mask_out, void *stream);
+
 /* ---- attention over a MATERIALISED embedding (module-level drop-in) ----------------------
  * ATTENTION.forward(mix_hidden[N,T,F,E], query[N,E|2E]) (EvalVer.py:210-226).
  * emb [Nb,TF,E]; emb_batch_stride = 0 shares one embedding across the S queries of an
