@@ -15,9 +15,7 @@
 //
 // Tile 128 x 256 x 64, 2 smem stages x (A_hi,A_lo,B_hi,B_lo) = 192 KB, 2 TMEM accumulator stages x
 // 256 columns; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
-#include "common.cuh"
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_ptx.cuh"
 #include <mutex>
 
 namespace dl4ss {
@@ -28,69 +26,6 @@ constexpr int TB_BYTES = TBN * TBK * 2;                       // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
 constexpr int TC_THREADS = 192;
 constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
-}
-// K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ------------------------------------------------------------------------------------------ split
 __global__ void __launch_bounds__(256)
@@ -286,8 +221,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+                        constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -338,11 +272,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encoder() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -355,34 +285,32 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+int make_bf16_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                  const cuuint32_t *box) {
+    EncodeTiledFn fn = tensor_map_encoder();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return DL4SS_ECUDA; }
+    return DL4SS_OK;
+}
+
 // planes: bf16 [2][R][Kp]; box = 64 (K) x rows x 1 plane, 128B swizzle, OOB rows zero-filled
 static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int Kp, int box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)R, 2};
     cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
     cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(planes), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) R=%lld Kp=%d", (int)r, R, Kp); return DL4SS_ECUDA; }
-    return DL4SS_OK;
+    return make_bf16_map(map, planes, 3, dims, strides, box);
 }
 
 // W planes bf16 [2][F*E][Kp] viewed as [2][F][E][Kp]; box = 64 (K) x 64 (E, rows >= E zero-filled) x 4 bins
 static int make_binned_map(CUtensorMap *map, const void *planes, int F, int E, int Kp) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)E, (cuuint64_t)F, 2};
     cuuint64_t strides[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)E * Kp * 2, (cuuint64_t)F * E * Kp * 2};
     cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)ATT_EP, (cuuint32_t)ATT_BINS, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(planes), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (binned) failed (%d)", (int)r); return DL4SS_ECUDA; }
-    return DL4SS_OK;
+    return make_bf16_map(map, planes, 4, dims, strides, box);
 }
 
 template <typename Epi>
