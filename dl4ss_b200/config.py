@@ -42,3 +42,7 @@ def sine_window(win_size=None):
 #            fp32 accumulation: masks within ~2e-6 of fp32 (the default);
 #   'fp32'   CUDA-core FMA, bit-close to an SGEMM (the yard-stick the tests compare 'bf16x3' with).
 GEMM_PRECISION = 'bf16x3'
+
+# Not in the reference: run the recurrent product h*W_hh^T on tcgen05 (persistent tensor-core kernel)
+# when GEMM_PRECISION == 'bf16x3' and H is supported; False selects the fp32 CUDA-core recurrent kernel.
+RNN_TENSOR_CORES = True

@@ -115,10 +115,17 @@ class _PackedRNN(object):
                     'wih': torch.cat(wih, 0).contiguous().float(),
                     'bias': torch.cat(bias, 0).contiguous().float(),
                     'whh': torch.stack(whh, 0).contiguous().float(),
+                    'whh2d': torch.cat(whh, 0).contiguous().float(),         # [2*G*H, H] for the bf16 split
                     'bhn': torch.stack(bhn, 0).contiguous().float() if gru else None,
                 })
         self.key, self.layers = key, layers
         return layers
+
+
+def use_tc_recurrence(H, cell):
+    """tcgen05 recurrent kernel: bf16x3 mode, supported H (multiple of 20, <= 320), not disabled."""
+    return (use_tensor_cores() and config.RNN_TENSOR_CORES
+            and bool(_lib.load().dl4ss_rnn_tc_supported(H, cell)))
 
 
 def rnn_forward(packed, x, save=None):
@@ -132,7 +139,11 @@ def rnn_forward(packed, x, save=None):
     H = rnn.hidden_size
     B, T, _ = x.shape
     dev = x.device
-    ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
+    tc_rec = use_tc_recurrence(H, cell)
+    if tc_rec:
+        ws_bytes = int(lib.dl4ss_rnn_tc_workspace_bytes(B, T, H, cell))
+    else:
+        ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
@@ -147,10 +158,16 @@ def rnn_forward(packed, x, save=None):
         if save is not None:
             gates = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
             cells = torch.empty(B, T, 2, H, device=dev, dtype=torch.float32)
-        rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
-                                     _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
-                                     _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
-        _lib.check(rc, 'dl4ss_rnn_layer_fwd')
+        if tc_rec:
+            rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(weight_planes(lw['whh2d']), torch.bfloat16),
+                                            _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                            _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
+            _lib.check(rc, 'dl4ss_rnn_layer_tc_fwd')
+        else:
+            rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
+                                         _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                         _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
+            _lib.check(rc, 'dl4ss_rnn_layer_fwd')
         if save is not None:
             save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
         inp = y

@@ -102,6 +102,19 @@ int dl4ss_rnn_layer_fwd(int cell, const float *xproj, const float *whh, const fl
                         float *y, int B, int T, int H, float *gates_save, float *cell_save,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- K3 on the tensor cores (tcgen05, bf16x3 split of h and W_hh, fp32 TMEM accumulation) -----------
+ * Same contract as dl4ss_rnn_layer_fwd except that W_hh arrives pre-split:
+ * whh_planes = dl4ss_split_bf16 of whh viewed as [2*G*H, H]  ->  bf16 [2 planes][2*G*H][Kp].
+ * Supported when dl4ss_rnn_tc_supported(H, cell) != 0 (H a multiple of 20, <= 320 -- every reference
+ * config uses 300); otherwise DL4SS_EUNSUPPORTED and the caller uses dl4ss_rnn_layer_fwd.
+ * workspace: dl4ss_rnn_tc_workspace_bytes() bytes, 256-byte aligned, zero-filled by the callee
+ * (release counters + the L2-resident bf16 exchange buffer the CTAs pass h_t through). */
+int    dl4ss_rnn_tc_supported(int H, int cell);
+size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
+int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
+                           float *y, int B, int T, int H, float *gates_save, float *cell_save,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- K4: Linear + tanh + speaker attention + mask, fused ---------------------------------
  * Replaces MIX_SPEECH.Linear+tanh (EvalVer.py:298-301), the S-fold expand().contiguous()
  * (:453-455), ATTENTION 'dot' (:216-226) and, for cRM, K*tanh + decompression
