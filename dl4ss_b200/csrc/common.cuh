@@ -52,7 +52,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 
 // accurate-enough fp32 transcendental helpers (abs err ~1e-7, far below the 1e-4 parity bar)
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }   // MUFU.EX2 + MUFU.RCP, ~2 ulp
 __device__ __forceinline__ float tanh_f(float x) {
     // tanh(x) = 1 - 2/(exp(2x)+1); saturates cleanly for |x| large
     float e = __expf(2.0f * x);

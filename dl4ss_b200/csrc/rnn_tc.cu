@@ -39,6 +39,8 @@ struct RnnTcParams {
     unsigned *counters;        // [2][tiles_total]
     int B, T, H, Kp, nkc, Bpad;
     int tile0, tiles, tiles_total, nslices;
+    long long *trace;          // optional [steps][16] clock stamps of CTA 0 (profiling hook), else null
+    int trace_steps;
 };
 
 __device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem) {
@@ -49,8 +51,13 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+// relaxed: the caller has just executed __threadfence() (fence + relaxed atomic = release pattern);
+// red.release would pay for a second MEMBAR
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned *p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stamp(const RnnTcParams &p, int s, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && s < p.trace_steps) p.trace[s * 16 + slot] = clock64();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
@@ -81,7 +88,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     constexpr int NCOL = G * RT_HS;                 // accumulator columns in use: 80 / 60
     constexpr int UN = (NCOL + 7) / 8 * 8;          // UMMA N: 80 / 64
     constexpr int WBLK = UN * 128;                  // bytes of one (k-chunk, plane) W block (multiple of 1024)
-    constexpr uint32_t IDESC = umma_idesc_bf16(RT_BT, UN);
+    constexpr uint32_t IDESC2 = umma_idesc_bf16(RT_BT, 2 * UN);   // h_hi x [W_hi ; W_lo] in one instruction
+    constexpr uint32_t IDESC1 = umma_idesc_bf16(RT_BT, UN);       // h_lo x W_hi
     static_assert(RT_EU == 10, "tmem_ld10 / store loops are written for 10 units per thread");
 
     extern __shared__ unsigned char smem_raw[];
@@ -118,7 +126,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -134,16 +142,19 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                 for (int pl = 0; pl < 2; ++pl)
                     tma_load_4d(Wsm + (size_t)(c * 2 + pl) * WBLK, &tmap_w, wfull, c * RT_KC, u0, dir * G, pl);
             for (int s = 1; s < T; ++s) {
-                const unsigned want = (unsigned)p.nslices * (unsigned)s;
-                while (ld_acquire_gpu(counter) < want) { __nanosleep(32); }
-                fence_proxy_async();
+                const unsigned want = (unsigned)(p.nslices * RT_EPI_WARPS) * (unsigned)s;
+                stamp(p, s, 0);
+                while (ld_acquire_gpu(counter) < want) { }
+                stamp(p, s, 1);
+                fence_proxy_async();                 // the group's generic-proxy stores -> this thread's TMA reads
+                stamp(p, s, 15);
                 const int pp = (s - 1) & 1;
                 const int z = (pp * 2 + dir) * 2;
                 for (int c = 0; c < nkc; ++c) {
-                    mbar_expect_tx(&hfull[c], 2 * RT_HBLK);
+                    mbar_expect_tx(&hfull[c], 2 * RT_HBLK);             // one box = both planes of the chunk
                     tma_load_3d(Hsm + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[c], c * RT_KC, row0, z);
-                    tma_load_3d(Hsm + (size_t)(c * 2 + 1) * RT_HBLK, &tmap_h, &hfull[c], c * RT_KC, row0, z + 1);
                 }
+                stamp(p, s, 2);
             }
         }
     } else if (warp == 1) {
@@ -156,19 +167,23 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                 for (int c = 0; c < nkc; ++c) {
                     mbar_wait(&hfull[c], (uint32_t)(s - 1) & 1u);
                     tc_fence_after();
+                    if (c == 0) stamp(p, s, 3);
+                    if (c == nkc - 1) stamp(p, s, 4);
                     const uint64_t a_hi = umma_desc_sw128(smem_u32(Hsm + (size_t)(c * 2) * RT_HBLK));
                     const uint64_t a_lo = umma_desc_sw128(smem_u32(Hsm + (size_t)(c * 2 + 1) * RT_HBLK));
                     const uint64_t b_hi = umma_desc_sw128(smem_u32(Wsm + (size_t)(c * 2) * WBLK));
-                    const uint64_t b_lo = umma_desc_sw128(smem_u32(Wsm + (size_t)(c * 2 + 1) * WBLK));
                     int ksteps = (H - c * RT_KC + 15) / 16;
                     if (ksteps > RT_KC / 16) ksteps = RT_KC / 16;
                     for (int k = 0; k < ksteps; ++k) {      // +32 B per 16-element k step (>>4 = 2)
-                        umma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, IDESC, (c | k) != 0);
-                        umma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, IDESC, 1);
-                        umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, IDESC, 1);
+                        // an M=64 UMMA costs ~85 cycles here whatever N is, so the two products that share
+                        // h_hi run as ONE instruction over the stacked [W_hi ; W_lo] rows (N = 2*UN):
+                        // columns [0,UN) = hi*hi, [UN,2UN) = hi*lo, [2UN,3UN) = lo*hi
+                        umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, IDESC2, (c | k) != 0);
+                        umma_bf16(tmem_base + 2 * UN, a_lo + 2 * k, b_hi + 2 * k, IDESC1, (c | k) != 0);
                     }
                 }
                 umma_commit(tfull);
+                stamp(p, s, 5);
             }
         }
     } else if (warp < 4) {
@@ -217,11 +232,20 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             if (s >= 1) {
                 mbar_wait(tfull, (uint32_t)(s - 1) & 1u);
                 tc_fence_after();
+                if (tid == 128) stamp(p, s, 6);
 #pragma unroll
-                for (int g = 0; g < G; ++g) tmem_ld10(taddr + g * RT_HS + RT_EU * ch, acc[g]);
+                for (int g = 0; g < G; ++g) {
+                    float a1[RT_EU], a2[RT_EU];
+                    tmem_ld10(taddr + UN + g * RT_HS + RT_EU * ch, a1);
+                    tmem_ld10(taddr + 2 * UN + g * RT_HS + RT_EU * ch, a2);
+                    tmem_ld10(taddr + g * RT_HS + RT_EU * ch, acc[g]);
+#pragma unroll
+                    for (int j = 0; j < RT_EU; ++j) acc[g][j] += a1[j] + a2[j];      // small terms first
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty);
+                if (tid == 128) stamp(p, s, 7);
             } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g)
@@ -229,6 +253,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                     for (int j = 0; j < RT_EU; ++j) acc[g][j] = 0.f;
             }
             mbar_wait(&xfull[buf], (uint32_t)(s >> 1) & 1u);
+            if (tid == 128) stamp(p, s, 8);
             const float *xr = Xsm + (size_t)buf * RT_BT * RT_XP + r * RT_XP + RT_EU * ch;
             float xv[G][RT_EU];
 #pragma unroll
@@ -265,23 +290,53 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                     aux[j] = hn;                                    // W_hn*h + b_hn, kept for backward
                 }
             }
-            if (active) {
-                float *yo = p.y + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + uc;
-#pragma unroll
-                for (int j = 0; j < RT_EU; j += 2) *reinterpret_cast<float2 *>(yo + j) = make_float2(hnew[j], hnew[j + 1]);
-                if (s + 1 < T) {
+            if (tid == 128) stamp(p, s, 9);
+            // publish h_t first (the group's next step hangs on it), the fp32 outputs follow off the critical path
+            if (s + 1 < T) {
+                if (active) {
                     const int pp = s & 1;
                     __nv_bfloat16 *hh = p.hbuf + ((size_t)((pp * 2 + dir) * 2) * p.Bpad + b) * p.Kp + uc;
                     __nv_bfloat16 *hl = hh + (size_t)p.Bpad * p.Kp;
+                    uint32_t ph[RT_EU / 2], pl[RT_EU / 2];
 #pragma unroll
                     for (int j = 0; j < RT_EU; j += 2) {
                         const __nv_bfloat16 h0 = __float2bfloat16_rn(hnew[j]), h1 = __float2bfloat16_rn(hnew[j + 1]);
                         const __nv_bfloat16 l0 = __float2bfloat16_rn(hnew[j] - __bfloat162float(h0));
                         const __nv_bfloat16 l1 = __float2bfloat16_rn(hnew[j + 1] - __bfloat162float(h1));
-                        *reinterpret_cast<uint32_t *>(hh + j) = pack_bf16x2(h0, h1);
-                        *reinterpret_cast<uint32_t *>(hl + j) = pack_bf16x2(l0, l1);
+                        ph[j / 2] = pack_bf16x2(h0, h1);
+                        pl[j / 2] = pack_bf16x2(l0, l1);
+                    }
+                    // 20 B per plane: 8+8+4 (column half 0, 8-byte aligned) or 4+8+8 (half 1): fewer L2 write
+                    // transactions for the release fence to wait on
+                    if (ch == 0) {
+                        *reinterpret_cast<uint2 *>(hh) = make_uint2(ph[0], ph[1]);
+                        *reinterpret_cast<uint2 *>(hh + 4) = make_uint2(ph[2], ph[3]);
+                        *reinterpret_cast<uint32_t *>(hh + 8) = ph[4];
+                        *reinterpret_cast<uint2 *>(hl) = make_uint2(pl[0], pl[1]);
+                        *reinterpret_cast<uint2 *>(hl + 4) = make_uint2(pl[2], pl[3]);
+                        *reinterpret_cast<uint32_t *>(hl + 8) = pl[4];
+                    } else {
+                        *reinterpret_cast<uint32_t *>(hh) = ph[0];
+                        *reinterpret_cast<uint2 *>(hh + 2) = make_uint2(ph[1], ph[2]);
+                        *reinterpret_cast<uint2 *>(hh + 6) = make_uint2(ph[3], ph[4]);
+                        *reinterpret_cast<uint32_t *>(hl) = pl[0];
+                        *reinterpret_cast<uint2 *>(hl + 2) = make_uint2(pl[1], pl[2]);
+                        *reinterpret_cast<uint2 *>(hl + 6) = make_uint2(pl[3], pl[4]);
                     }
                 }
+                if (tid == 128) stamp(p, s, 10);
+                __syncwarp();
+                if (lane == 0) {                 // every epilogue warp releases its own rows: no CTA barrier
+                    __threadfence();
+                    if (tid == 128) stamp(p, s, 13);
+                    red_relaxed_gpu_add(counter, 1u);
+                    if (tid == 128) stamp(p, s, 14);
+                }
+            }
+            if (active) {
+                float *yo = p.y + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + uc;
+#pragma unroll
+                for (int j = 0; j < RT_EU; j += 2) *reinterpret_cast<float2 *>(yo + j) = make_float2(hnew[j], hnew[j + 1]);
                 if (p.gates_save != nullptr) {
                     float *go = p.gates_save + (((size_t)b * T + t) * 2 + dir) * GH + uc;
 #pragma unroll
@@ -296,21 +351,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                     for (int j = 0; j < RT_EU; j += 2) *reinterpret_cast<float2 *>(co + j) = make_float2(aux[j], aux[j + 1]);
                 }
             }
-            if (s + 1 < T) {
-                fence_proxy_async();                                  // generic-proxy stores -> TMA reads by the group
-                asm volatile("bar.sync 1, %0;\n" ::"n"(32 * RT_EPI_WARPS) : "memory");
-                if (tid == 128) {
-                    __threadfence();
-                    red_release_gpu_add(counter, 1u);
-                }
-            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -347,7 +394,7 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int rows_left, c
     {   // h exchange bf16 [8 = pp,dir,plane][Bpad][Kp]: box = 64 k x 64 rows
         cuuint64_t dims[3] = {(cuuint64_t)p.Kp, (cuuint64_t)p.Bpad, 8};
         cuuint64_t strides[2] = {(cuuint64_t)p.Kp * 2, (cuuint64_t)p.Bpad * p.Kp * 2};
-        cuuint32_t box[3] = {RT_KC, RT_BT, 1};
+        cuuint32_t box[3] = {RT_KC, RT_BT, 2};
         int rc = make_bf16_map(&mh, p.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
@@ -357,11 +404,20 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int rows_left, c
     return DL4SS_OK;
 }
 
+static long long *g_trace = nullptr;
+static int g_trace_steps = 0;
+
 static bool rnn_tc_supported(int H) { return H >= RT_HS && H % RT_HS == 0 && H <= RT_MAXKC * RT_KC; }
 
 }  // namespace dl4ss
 
 using namespace dl4ss;
+
+// profiling hook: device buffer of steps*16 int64 receiving CTA 0's per-phase clock64() stamps (null = off)
+extern "C" void dl4ss_rnn_tc_set_trace(void *dev_buf, int steps) {
+    g_trace = (long long *)dev_buf;
+    g_trace_steps = dev_buf ? steps : 0;
+}
 
 extern "C" int dl4ss_rnn_tc_supported(int H, int cell) {
     return (cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU) && rnn_tc_supported(H) ? 1 : 0;
@@ -409,6 +465,7 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
     const size_t ctr = ((size_t)2 * p.tiles_total * sizeof(unsigned) + 255) / 256 * 256;
     p.hbuf = (__nv_bfloat16 *)((unsigned char *)workspace + ctr);
     p.tiles = 0;
+    p.trace = g_trace; p.trace_steps = g_trace_steps;
     int b0 = 0;
     while (b0 < B) {
         p.tile0 = b0 / RT_BT;

@@ -110,6 +110,9 @@ int dl4ss_rnn_layer_fwd(int cell, const float *xproj, const float *whh, const fl
  * workspace: dl4ss_rnn_tc_workspace_bytes() bytes, 256-byte aligned, zero-filled by the callee
  * (release counters + the L2-resident bf16 exchange buffer the CTAs pass h_t through). */
 int    dl4ss_rnn_tc_supported(int H, int cell);
+/* profiling hook: device buffer of steps*16 int64 that receives CTA 0's per-phase clock64() stamps of
+ * subsequent dl4ss_rnn_layer_tc_fwd launches (NULL switches it off; off by default) */
+void   dl4ss_rnn_tc_set_trace(void *dev_buf, int steps);
 size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
 int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
                            float *y, int B, int T, int H, float *gates_save, float *cell_save,
