@@ -149,8 +149,8 @@ def stage_times(sep, wav, idx, reps=3):
             G, H = 4 if W['cell'] == 'lstm' else 3, W['H']
             from dl4ss_b200 import _lib
             cell = _lib.CELL_LSTM if W['cell'] == 'lstm' else _lib.CELL_GRU
-            ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
-            ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+            tc_rec = M.use_tc_recurrence(H, cell)
+            ws = M.recurrent_workspace(B, T, H, cell, tc_rec, x.device)
             xproj = torch.empty(B * T, 2 * G * H, device=x.device)
             inp = x
             for lw in packed.get():
@@ -162,11 +162,7 @@ def stage_times(sep, wav, idx, reps=3):
                 else:
                     M.linear_fwd(x2d, lw['wih'], lw['bias'], 'none', out=xproj)
                 e1.record()
-                y = torch.empty(B, T, 2 * H, device=x.device)
-                rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
-                                             _lib.ptr(y), B, T, H, None, None, _lib.ptr(ws, torch.uint8), ws_bytes,
-                                             _lib.stream())
-                _lib.check(rc, 'rnn')
+                y = M.recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec)
                 e2.record(); torch.cuda.synchronize()
                 t['rnn_xproj'] += e0.elapsed_time(e1); t['rnn_recurrent'] += e1.elapsed_time(e2)
                 inp = y
@@ -372,7 +368,7 @@ def main():
                 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
                 'launches_per_step': n_launch, 'ms_per_step': st[dom],
-                'note': 'algorithmic fp32 FLOPs; tensor-core stages run bf16x3 (3 MMAs per product), the recurrent stage is CUDA-core FMA'}
+                'note': 'algorithmic fp32 FLOPs; every tensor-core stage runs bf16x3 (3 MMA products per fp32 product); the recurrent stage is a latency chain of T sequential steps per layer, not throughput bound (DESIGN.md 4)'}
         stages = {}
         for k, by in (('stft', alg['stft_bytes']), ('mask_istft', alg['istft_bytes'])):
             a = by / (st[k] * 1e-3) / 1e9

@@ -128,6 +128,29 @@ def use_tc_recurrence(H, cell):
             and bool(_lib.load().dl4ss_rnn_tc_supported(H, cell)))
 
 
+def recurrent_workspace(B, T, H, cell, tc_rec, device):
+    lib = _lib.load()
+    n = int(lib.dl4ss_rnn_tc_workspace_bytes(B, T, H, cell) if tc_rec else lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
+    return torch.empty(n, device=device, dtype=torch.uint8)
+
+
+def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None):
+    """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]."""
+    lib = _lib.load()
+    y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
+    if tc_rec:
+        rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(weight_planes(lw['whh2d']), torch.bfloat16),
+                                        _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                        _lib.ptr(ws, torch.uint8), ws.numel(), _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_layer_tc_fwd')
+    else:
+        rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
+                                     _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                     _lib.ptr(ws, torch.uint8), ws.numel(), _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_layer_fwd')
+    return y
+
+
 def rnn_forward(packed, x, save=None):
     """Bidirectional multi-layer LSTM/GRU forward, batch_first, zero initial state.
     x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward."""
@@ -140,11 +163,7 @@ def rnn_forward(packed, x, save=None):
     B, T, _ = x.shape
     dev = x.device
     tc_rec = use_tc_recurrence(H, cell)
-    if tc_rec:
-        ws_bytes = int(lib.dl4ss_rnn_tc_workspace_bytes(B, T, H, cell))
-    else:
-        ws_bytes = int(lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
-    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    ws = recurrent_workspace(B, T, H, cell, tc_rec, dev)
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
     for lw in packed.get():
@@ -153,21 +172,11 @@ def rnn_forward(packed, x, save=None):
             linear_tc(split_bf16(x2d), weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
         else:
             linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
-        y = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
         gates = cells = None
         if save is not None:
             gates = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
             cells = torch.empty(B, T, 2, H, device=dev, dtype=torch.float32)
-        if tc_rec:
-            rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(weight_planes(lw['whh2d']), torch.bfloat16),
-                                            _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
-                                            _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
-            _lib.check(rc, 'dl4ss_rnn_layer_tc_fwd')
-        else:
-            rc = lib.dl4ss_rnn_layer_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
-                                         _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
-                                         _lib.ptr(ws, torch.uint8), ws_bytes, _lib.stream())
-            _lib.check(rc, 'dl4ss_rnn_layer_fwd')
+        y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells)
         if save is not None:
             save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
         inp = y
