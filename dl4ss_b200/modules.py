@@ -115,7 +115,6 @@ class _PackedRNN(object):
                     'wih': torch.cat(wih, 0).contiguous().float(),
                     'bias': torch.cat(bias, 0).contiguous().float(),
                     'whh': torch.stack(whh, 0).contiguous().float(),
-                    'whh2d': torch.cat(whh, 0).contiguous().float(),         # [2*G*H, H] for the bf16 split
                     'bhn': torch.stack(bhn, 0).contiguous().float() if gru else None,
                 })
         self.key, self.layers = key, layers
@@ -134,12 +133,25 @@ def recurrent_workspace(B, T, H, cell, tc_rec, device):
     return torch.empty(n, device=device, dtype=torch.uint8)
 
 
+def whh_planes(lw, cell, H):
+    """Packed bf16 hi/lo planes of W_hh for the tcgen05 recurrent kernel (built once per weight version:
+    `lw` is rebuilt by _PackedRNN whenever a parameter changes)."""
+    pl = lw.get('whh_tc')
+    if pl is None:
+        lib = _lib.load()
+        pl = torch.empty(int(lib.dl4ss_rnn_tc_whh_bytes(H)) // 2, device=lw['whh'].device, dtype=torch.bfloat16)
+        rc = lib.dl4ss_rnn_tc_pack_whh(cell, _lib.ptr(lw['whh']), H, _lib.ptr(pl, torch.bfloat16), _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_tc_pack_whh')
+        lw['whh_tc'] = pl
+    return pl
+
+
 def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None):
     """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]."""
     lib = _lib.load()
     y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
     if tc_rec:
-        rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(weight_planes(lw['whh2d']), torch.bfloat16),
+        rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(whh_planes(lw, cell, H), torch.bfloat16),
                                         _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
                                         _lib.ptr(ws, torch.uint8), ws.numel(), _lib.stream())
         _lib.check(rc, 'dl4ss_rnn_layer_tc_fwd')

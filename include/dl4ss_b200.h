@@ -103,8 +103,10 @@ int dl4ss_rnn_layer_fwd(int cell, const float *xproj, const float *whh, const fl
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- K3 on the tensor cores (tcgen05, bf16x3 split of h and W_hh, fp32 TMEM accumulation) -----------
- * Same contract as dl4ss_rnn_layer_fwd except that W_hh arrives pre-split:
- * whh_planes = dl4ss_split_bf16 of whh viewed as [2*G*H, H]  ->  bf16 [2 planes][2*G*H][Kp].
+ * Same contract as dl4ss_rnn_layer_fwd except that W_hh arrives pre-packed by dl4ss_rnn_tc_pack_whh:
+ * whh [2,G*H,H] fp32 -> bf16 hi/lo planes [2][2 dir * 4H rows][Kp], row dir*4H + 4*u + g = gate g of
+ * unit u (the unit-major order the kernel's epilogue transposes inside 4-lane groups; GRU's 4th row is
+ * zero), dl4ss_rnn_tc_whh_bytes(H) bytes, 16-byte aligned.  Pack once per weight update.
  * Supported when dl4ss_rnn_tc_supported(H, cell) != 0 (H a multiple of 20, <= 320 -- every reference
  * config uses 300); otherwise DL4SS_EUNSUPPORTED and the caller uses dl4ss_rnn_layer_fwd.
  * workspace: dl4ss_rnn_tc_workspace_bytes() bytes, 256-byte aligned, zero-filled by the callee
@@ -113,6 +115,8 @@ int    dl4ss_rnn_tc_supported(int H, int cell);
 /* profiling hook: device buffer of steps*16 int64 that receives CTA 0's per-phase clock64() stamps of
  * subsequent dl4ss_rnn_layer_tc_fwd launches (NULL switches it off; off by default) */
 void   dl4ss_rnn_tc_set_trace(void *dev_buf, int steps);
+size_t dl4ss_rnn_tc_whh_bytes(int H);
+int    dl4ss_rnn_tc_pack_whh(int cell, const float *whh, int H, void *planes, void *stream);
 size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
 int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
                            float *y, int B, int T, int H, float *gates_save, float *cell_save,

@@ -11,7 +11,8 @@ from tests.util import build_pair
 dev = torch.device('cuda:0')
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = 313
-ref, ours = build_pair('lstm', 1, 129, T, False)
+CELL = sys.argv[2] if len(sys.argv) > 2 else 'lstm'
+ref, ours = build_pair(CELL, 1, 129, T, False)
 x = torch.rand(B, T, 129, device=dev)
 lib = _lib.load()
 steps = 64
@@ -25,7 +26,7 @@ with torch.no_grad():
     lib.dl4ss_rnn_tc_set_trace(None, 0)
 t = buf.cpu().numpy().reshape(steps, 16)
 names = ['poll_start', 'poll_done', 'tma_issued', 'h0_landed', 'hlast_landed', 'mma_committed', 'tfull_seen', 'tmem_read',
-         'xfull_seen', 'math_done', 'stores_done', 'proxy_fence', 'bar_done', 'threadfence', 'red_done', 'cons_fence']
+         'transposed', 'math_done', 'stores_done', 'xfull_seen', 'x_read', 'threadfence', 'red_done', 'unused']
 print('step-to-step (poll_done) cycles:', np.diff(t[10:60, 1]).mean())
 base = t[10:60, 1:2]
 rel = (t[10:60, :16] - base).astype(np.float64)
