@@ -62,6 +62,7 @@ struct EpiPlain {
     float *C;
     const float *bias;
     int ldc;
+    int act;             // DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID
 };
 struct EpiAttn {
     const float *bias;   // [F*E]
@@ -87,6 +88,10 @@ __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float c
 }
 
 // one accumulator row (this thread's TMEM lane) -> global
+__device__ __forceinline__ float apply_act(float x, int act) {
+    return act == DL4SS_ACT_TANH ? tanh_f(x) : act == DL4SS_ACT_SIGMOID ? sigmoid_f(x) : x;
+}
+
 __device__ __forceinline__ void epilogue_row(const EpiPlain &e, uint32_t taddr, int m, int n0, int M, int N) {
     float *crow = e.C + (size_t)m * e.ldc;
     const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
@@ -101,15 +106,15 @@ __device__ __forceinline__ void epilogue_row(const EpiPlain &e, uint32_t taddr, 
         for (int j = 0; j < 16; j += 4) {
             if (vec && n + j + 3 < N) {
                 float4 o;
-                o.x = v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
-                o.y = v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f);
-                o.z = v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f);
-                o.w = v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f);
+                o.x = apply_act(v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f), e.act);
+                o.y = apply_act(v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f), e.act);
+                o.z = apply_act(v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f), e.act);
+                o.w = apply_act(v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f), e.act);
                 *reinterpret_cast<float4 *>(crow + n + j) = o;
             } else {
 #pragma unroll
                 for (int jj = j; jj < j + 4; ++jj)
-                    if (n + jj < N) crow[n + jj] = v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f);
+                    if (n + jj < N) crow[n + jj] = apply_act(v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f), e.act);
             }
         }
     }
@@ -359,11 +364,12 @@ extern "C" int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void
 }
 
 extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C, int ldc,
-                                   int M, int N, int K, void *stream) {
+                                   int M, int N, int K, int act, void *stream) {
     DL4SS_CHECK_ARG(a_planes && w_planes && C, "linear_tc_fwd: null operand");
     DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "linear_tc_fwd: bad M/N/K/ldc %d/%d/%d/%d", M, N, K, ldc);
     if (M == 0) return DL4SS_OK;
-    EpiPlain e{C, bias, ldc};
+    DL4SS_CHECK_ARG(act >= DL4SS_ACT_NONE && act <= DL4SS_ACT_SIGMOID, "linear_tc_fwd: bad act %d", act);
+    EpiPlain e{C, bias, ldc, act};
     return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), e, (cudaStream_t)stream);
 }
 

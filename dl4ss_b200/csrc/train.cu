@@ -1,0 +1,251 @@
+// Backward-side kernels of the training step (STFT -> encoder -> masks -> MSE loss -> backward):
+//   dl4ss_mask_loss_bwd   d(loss)/d(mask) of the reference objective
+//                         (TDAA_beta/main_run_sstune_EvalVer.py:641,659-666 ; cRM ...cRM_EvalVer.py:566-568,741-743)
+//   dl4ss_attn_dot_bwd    backward of ATTENTION 'dot' + sigmoid (| cRM) + the tanh of MIX_SPEECH.Linear:
+//                         d(mask) -> d(pre-tanh embedding) and d(speaker query) in one pass over emb[.,TF,E]
+//   dl4ss_rnn_bwd_step    one time step of BPTT gate arithmetic for a bidirectional LSTM / GRU layer
+//                         (nn.LSTM / nn.GRU autograd in the reference, :673 `loss.backward()`).
+// The dense contractions of the backward pass (dW, dx, dh, and the per-step dh_rec = dgates * W_hh) are plain
+// GEMMs issued by the host code through cuBLAS this round; everything fused or element-wise is here.
+#include "common.cuh"
+
+namespace dl4ss {
+
+// ----------------------------------------------------------------------------------------- loss backward
+template <int MASK_KIND>
+__global__ void __launch_bounds__(256)
+mask_loss_bwd_kernel(const float *__restrict__ mask, const float *__restrict__ mix, const float *__restrict__ target,
+                     int S, long long TF, long long total, float c0, float c1, float *__restrict__ dmask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / TF, tf = i - b * TF;
+        if (MASK_KIND == DL4SS_MASK_REAL) {
+            const float x = mix[i];
+            float sum = 0.f;
+            for (int s = 0; s < S; ++s) sum += mask[(b * S + s) * TF + tf];
+            const float g1 = c1 * (sum - 1.0f);
+            for (int s = 0; s < S; ++s) {
+                const long long j = (b * S + s) * TF + tf;
+                dmask[j] = fmaf(c0 * (mask[j] * x - target[j]), x, g1);
+            }
+        } else {
+            const float2 x = reinterpret_cast<const float2 *>(mix)[i];
+            for (int s = 0; s < S; ++s) {
+                const long long j = (b * S + s) * TF + tf;
+                const float2 m = reinterpret_cast<const float2 *>(mask)[j];
+                const float2 y = reinterpret_cast<const float2 *>(target)[j];
+                const float dr = c0 * ((m.x * x.x - m.y * x.y) - y.x);
+                const float di = c1 * ((m.x * x.y + m.y * x.x) - y.y);
+                reinterpret_cast<float2 *>(dmask)[j] = make_float2(dr * x.x + di * x.y, di * x.x - dr * x.y);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------- attention backward
+constexpr int AB_ROWS = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(AB_ROWS)
+attn_dot_bwd_kernel(const float *__restrict__ emb, const float *__restrict__ q, const float *__restrict__ mask,
+                    const float *__restrict__ dmask, int S, int TF, int E, float crm_k, float crm_c,
+                    float *__restrict__ dz, float *__restrict__ dq) {
+    extern __shared__ __align__(16) float sm[];
+    const int NQ = (MODE == DL4SS_ATT_DOT_CRM) ? 2 : 1;        // energies per speaker
+    const int EQ = NQ * E;
+    const int EP = E | 1;                                      // odd row pitch: conflict-free row-per-thread access
+    float *tile = sm;                                          // AB_ROWS * EP   emb rows -> dz rows
+    float *qs = tile + AB_ROWS * EP;                           // S * EQ
+    float *de = qs + S * EQ;                                   // S * NQ * AB_ROWS
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * AB_ROWS;
+    const int nrows = min(AB_ROWS, TF - r0);
+    const int tid = threadIdx.x;
+
+    const float *src = emb + ((size_t)b * TF + r0) * E;
+    for (int i = tid; i < nrows * E; i += AB_ROWS) tile[(i / E) * EP + (i % E)] = src[i];
+    for (int i = tid; i < S * EQ; i += AB_ROWS) qs[i] = q[(size_t)b * S * EQ + i];
+    __syncthreads();
+
+    float dev[8];                                              // S * NQ <= 8 energies per row
+    if (tid < nrows) {
+        const size_t tf = (size_t)r0 + tid;
+        for (int s = 0; s < S; ++s) {
+            const size_t j = ((size_t)b * S + s) * TF + tf;
+            if (MODE == DL4SS_ATT_DOT) {
+                const float m = mask[j];
+                dev[s] = dmask[j] * m * (1.0f - m);
+            } else {
+                const float2 m = reinterpret_cast<const float2 *>(mask)[j];
+                const float2 g = reinterpret_cast<const float2 *>(dmask)[j];
+                if (crm_c > 0.f) {     // M = -1/C log((K-m)/(K+m)), m = K tanh(e)  =>  dM/de = 2/C
+                    dev[2 * s] = g.x * (2.0f / crm_c);
+                    dev[2 * s + 1] = g.y * (2.0f / crm_c);
+                } else {               // compressed mask K tanh(e): d/de = K - m^2/K
+                    dev[2 * s] = g.x * (crm_k - m.x * m.x / crm_k);
+                    dev[2 * s + 1] = g.y * (crm_k - m.y * m.y / crm_k);
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < S * NQ; ++i) dev[i] = 0.f;
+    }
+    for (int i = 0; i < S * NQ; ++i) de[i * AB_ROWS + tid] = dev[i];
+    __syncthreads();
+    // dq[s][e] = sum_rows de[s][row] * emb[row][e]   (emb still in the tile)
+    for (int i = tid; i < S * EQ; i += AB_ROWS) {
+        const int sq = i / E, e = i - sq * E;                  // sq = s*NQ + component
+        const float *d = de + sq * AB_ROWS;
+        float acc = 0.f;
+        for (int r = 0; r < nrows; ++r) acc = fmaf(d[r], tile[r * EP + e], acc);
+        // q layout [S][NQ*E]: speaker s, component c -> s*EQ + c*E + e == sq*E + e
+        atomicAdd(dq + (size_t)b * S * EQ + (size_t)sq * E + e, acc);
+    }
+    __syncthreads();
+    // dz[row][e] = (sum_s de_s * q_s[e]) * (1 - emb^2), in place in the tile
+    if (tid < nrows) {
+        float *row = tile + tid * EP;
+        for (int e = 0; e < E; ++e) {
+            float acc = 0.f;
+            for (int i = 0; i < S * NQ; ++i) acc = fmaf(dev[i], qs[i * E + e], acc);
+            const float x = row[e];
+            row[e] = acc * (1.0f - x * x);
+        }
+    }
+    __syncthreads();
+    float *dst = dz + ((size_t)b * TF + r0) * E;
+    for (int i = tid; i < nrows * E; i += AB_ROWS) dst[i] = tile[(i / E) * EP + (i % E)];
+}
+
+// ----------------------------------------------------------------------------------------- BPTT step
+template <int CELL>
+__global__ void __launch_bounds__(256)
+rnn_bwd_step_kernel(int s, const float *__restrict__ dy, const float *__restrict__ dh_rec,
+                    const float *__restrict__ gates, const float *__restrict__ cells, const float *__restrict__ y,
+                    float *__restrict__ carry, float *__restrict__ dgx, float *__restrict__ dgh,
+                    float *__restrict__ dg_cur, int B, int T, int H) {
+    constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+    const long long total = 2ll * B * H;
+    const size_t GH = (size_t)G * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(i % H);
+        const int b = (int)((i / H) % B);
+        const int dir = (int)(i / ((long long)H * B));
+        const int t = dir ? s : (T - 1 - s);                   // backward walks the forward order in reverse
+        const int tp = dir ? t + 1 : t - 1;                    // the step the forward pass came from
+        const bool has_prev = (tp >= 0 && tp < T);
+        const size_t st = (size_t)dir * B * H + (size_t)b * H + u;        // [2,B,H] state index
+        const size_t row = ((size_t)b * T + t) * 2 + dir;
+        float dh = dy[((size_t)b * T + t) * 2 * H + (size_t)dir * H + u];
+        if (s > 0) dh += dh_rec[st];
+        const float *gr = gates + row * GH + u;
+        float *ox = dgx + row * GH + u;
+        float *oc = dg_cur + ((size_t)dir * B + b) * GH + u;
+        if constexpr (CELL == DL4SS_CELL_LSTM) {
+            const float ig = gr[0], fg = gr[H], gg = gr[2 * (size_t)H], og = gr[3 * (size_t)H];
+            const float c = cells[row * H + u];
+            const float cp = has_prev ? cells[(((size_t)b * T + tp) * 2 + dir) * H + u] : 0.f;
+            const float tc = tanhf(c);
+            float dc = dh * og * (1.0f - tc * tc);
+            if (s > 0) dc += carry[st];
+            const float dai = dc * gg * ig * (1.0f - ig);
+            const float daf = dc * cp * fg * (1.0f - fg);
+            const float dag = dc * ig * (1.0f - gg * gg);
+            const float dao = dh * tc * og * (1.0f - og);
+            carry[st] = dc * fg;
+            ox[0] = dai; ox[H] = daf; ox[2 * (size_t)H] = dag; ox[3 * (size_t)H] = dao;
+            oc[0] = dai; oc[H] = daf; oc[2 * (size_t)H] = dag; oc[3 * (size_t)H] = dao;
+        } else {
+            if (s > 0) dh += carry[st];                        // the z * h_{t-1} path
+            const float rg = gr[0], zg = gr[H], ng = gr[2 * (size_t)H];
+            const float hn = cells[row * H + u];               // W_hn h + b_hn saved by the forward kernel
+            const float hp = has_prev ? y[((size_t)b * T + tp) * 2 * H + (size_t)dir * H + u] : 0.f;
+            const float dn = dh * (1.0f - zg);
+            const float dan = dn * (1.0f - ng * ng);
+            const float dar = dan * hn * rg * (1.0f - rg);
+            const float daz = dh * (hp - ng) * zg * (1.0f - zg);
+            const float dhn = dan * rg;
+            carry[st] = dh * zg;
+            float *oh = dgh + row * GH + u;
+            ox[0] = dar; ox[H] = daz; ox[2 * (size_t)H] = dan;
+            oh[0] = dar; oh[H] = daz; oh[2 * (size_t)H] = dhn;
+            oc[0] = dar; oc[H] = daz; oc[2 * (size_t)H] = dhn;
+        }
+    }
+}
+
+}  // namespace dl4ss
+
+using namespace dl4ss;
+
+extern "C" int dl4ss_mask_loss_bwd(const float *mask, int mask_kind, const float *mix, const float *target, int B,
+                                   int S, int TF, float c0, float c1, float *dmask, void *stream) {
+    DL4SS_CHECK_ARG(mask && mix && target && dmask, "mask_loss_bwd: null operand");
+    DL4SS_CHECK_ARG(mask_kind == DL4SS_MASK_REAL || mask_kind == DL4SS_MASK_COMPLEX, "mask_loss_bwd: bad mask_kind %d", mask_kind);
+    DL4SS_CHECK_ARG(B >= 0 && S >= 1 && TF >= 1, "mask_loss_bwd: bad B/S/TF");
+    if (B == 0) return DL4SS_OK;
+    const long long total = (long long)B * TF;
+    long long blocks = cdivll(total, 256);
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (mask_kind == DL4SS_MASK_REAL)
+        mask_loss_bwd_kernel<DL4SS_MASK_REAL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, mix, target, S, TF, total, c0, c1, dmask);
+    else
+        mask_loss_bwd_kernel<DL4SS_MASK_COMPLEX><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, mix, target, S, TF, total, c0, c1, dmask);
+    DL4SS_LAUNCH_CHECK("mask_loss_bwd_kernel");
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                                  int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
+                                  void *stream) {
+    DL4SS_CHECK_ARG(emb && q && mask && dmask && dz && dq, "attn_dot_bwd: null operand");
+    DL4SS_CHECK_ARG(mode == DL4SS_ATT_DOT || mode == DL4SS_ATT_DOT_CRM, "attn_dot_bwd: bad mode %d", mode);
+    const int NQ = (mode == DL4SS_ATT_DOT_CRM) ? 2 : 1;
+    DL4SS_CHECK_ARG(B >= 0 && S >= 1 && S * NQ <= 8 && TF >= 1 && E >= 1, "attn_dot_bwd: bad shape (S*%d <= 8)", NQ);
+    if (B == 0) return DL4SS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DL4SS_CUDA(cudaMemsetAsync(dq, 0, (size_t)B * S * NQ * E * sizeof(float), st));
+    const size_t smem = ((size_t)AB_ROWS * (E | 1) + (size_t)S * NQ * E + (size_t)S * NQ * AB_ROWS) * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("attn_dot_bwd: E=%d S=%d needs %zu B of shared memory", E, S, smem);
+        return DL4SS_EUNSUPPORTED;
+    }
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0 < 65535) ? B - b0 : 65535;
+        dim3 grid(cdiv(TF, AB_ROWS), nb);
+        const size_t mo = (size_t)b0 * S * TF * NQ;
+#define LAUNCH_AB(MODE)                                                                                          \
+        do {                                                                                                     \
+            DL4SS_CUDA(cudaFuncSetAttribute(attn_dot_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attn_dot_bwd_kernel<MODE><<<grid, AB_ROWS, smem, st>>>(emb + (size_t)b0 * TF * E, q + (size_t)b0 * S * NQ * E, \
+                mask + mo, dmask + mo, S, TF, E, crm_k, crm_c, dz + (size_t)b0 * TF * E, dq + (size_t)b0 * S * NQ * E); \
+        } while (0)
+        if (mode == DL4SS_ATT_DOT) LAUNCH_AB(DL4SS_ATT_DOT); else LAUNCH_AB(DL4SS_ATT_DOT_CRM);
+#undef LAUNCH_AB
+        DL4SS_LAUNCH_CHECK("attn_dot_bwd_kernel");
+    }
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, const float *gates_save,
+                                  const float *cell_save, const float *y, float *carry, float *dgx, float *dgh,
+                                  float *dg_cur, int B, int T, int H, void *stream) {
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_bwd_step: bad cell %d", cell);
+    DL4SS_CHECK_ARG(dy && gates_save && cell_save && carry && dgx && dg_cur, "rnn_bwd_step: null operand");
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || (y && dgh), "rnn_bwd_step: GRU needs y and dgh");
+    DL4SS_CHECK_ARG(s == 0 || dh_rec, "rnn_bwd_step: dh_rec is null");
+    DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && s >= 0 && s < T, "rnn_bwd_step: bad B/T/H/s");
+    if (B == 0) return DL4SS_OK;
+    const long long total = 2ll * B * H;
+    long long blocks = cdivll(total, 256);
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (cell == DL4SS_CELL_LSTM)
+        rnn_bwd_step_kernel<DL4SS_CELL_LSTM><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            s, dy, dh_rec, gates_save, cell_save, y, carry, dgx, dgh, dg_cur, B, T, H);
+    else
+        rnn_bwd_step_kernel<DL4SS_CELL_GRU><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            s, dy, dh_rec, gates_save, cell_save, y, carry, dgx, dgh, dg_cur, B, T, H);
+    DL4SS_LAUNCH_CHECK("rnn_bwd_step_kernel");
+    return DL4SS_OK;
+}

@@ -63,13 +63,14 @@ def weight_planes(w):
     return ent[2]
 
 
-def linear_tc(a_planes, w_planes, bias, M, N, K, out=None):
-    """a[M,K] @ w[N,K]^T + bias from pre-split planes on tcgen05 (bf16x3, fp32 accumulate)."""
+def linear_tc(a_planes, w_planes, bias, M, N, K, out=None, act='none'):
+    """act(a[M,K] @ w[N,K]^T + bias) from pre-split planes on tcgen05 (bf16x3, fp32 accumulate)."""
     lib = _lib.load()
     if out is None:
         out = torch.empty(M, N, device=a_planes.device, dtype=torch.float32)
+    a = {'none': _lib.ACT_NONE, 'tanh': _lib.ACT_TANH, 'sigmoid': _lib.ACT_SIGMOID}[act]
     rc = lib.dl4ss_linear_tc_fwd(_lib.ptr(a_planes, torch.bfloat16), _lib.ptr(w_planes, torch.bfloat16),
-                                 _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0), M, N, K, _lib.stream())
+                                 _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0), M, N, K, a, _lib.stream())
     _lib.check(rc, 'dl4ss_linear_tc_fwd')
     return out
 

@@ -1,0 +1,258 @@
+"""Training step of the separation path on the GPU: forward with saved activations, loss, backward,
+(sharded) gradient all-reduce, optimizer step.
+
+Mirrors one iteration of the reference's training loop
+(TDAA_beta/main_run_sstune_EvalVer.py:586-675 ; cRM: TDAA_beta/main_run_sstune_cRM_EvalVer.py:645-753):
+    feas -> MIX_SPEECH -> SPEECH_EMBEDDING (+ADDJUST) -> ATTENTION -> masks -> mask*mix -> MSELoss
+    (+0.5*MSE(sum_s mask, 1)) -> zero_grad -> backward -> Adam.step
+without the discriminator terms (out of scope).  The forward runs the same CUDA kernels
+as inference (tcgen05 projections, persistent recurrent kernel) with the gate activations saved; the
+backward is written out by hand: fused CUDA kernels for the loss / attention / BPTT gate arithmetic
+(csrc/train.cu) and plain library GEMMs (torch.matmul -> cuBLAS fp32) for the dense contractions
+dW, dx, dh and the per-step dh_rec = dgates x W_hh.  Gradients land in the parameters' `.grad`, so any
+torch optimizer (the reference uses Adam, lr 2e-4) steps them.
+
+Utterances shard by batch across ranks: every rank runs the step on its shard with the
+loss normalised by the GLOBAL element count, then one all-reduce (sum) of the flat fp32 gradient
+bucket reproduces the global-batch MSELoss gradients on every rank.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+from . import config
+from . import modules as M
+
+
+def shard_range(n, rank, world):
+    """Contiguous utterance shard [lo, hi) of rank `rank` (first n % world ranks get one extra)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def flatten_grads(params):
+    """One contiguous fp32 bucket of every parameter's gradient (zeros where a grad is None)."""
+    params = [p for p in params if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
+    o = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is not None:
+            flat[o:o + n].copy_(p.grad.reshape(-1))
+        o += n
+    return flat
+
+
+def unflatten_grads(flat, params):
+    o = 0
+    for p in params:
+        if not p.requires_grad:
+            continue
+        n = p.numel()
+        g = flat[o:o + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        o += n
+
+
+def allreduce_gradients(params, group=None):
+    """Sum the gradients over ranks through ONE flat bucket (NCCL over NVLink on the GPU box, gloo in the
+    CPU tests).  Returns the number of bytes reduced.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    params = [p for p in params if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    flat = flatten_grads(params)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    unflatten_grads(flat, params)
+    return flat.numel() * 4
+
+
+def _accum(p, g):
+    g = g.reshape(p.shape).to(p.dtype)
+    if p.grad is None:
+        p.grad = g.clone()
+    else:
+        p.grad.add_(g)
+
+
+class TrainStep(object):
+    """loss_and_grads(mix_feas, spk_idx, target[, mix_mag]) -> loss tensors; parameter grads accumulated."""
+
+    def __init__(self, mix_hidden_layer_3d, mix_speech_multiEmbedding, att_speech_layer, adjust_layer=None):
+        if att_speech_layer.mode != 'dot':
+            raise NotImplementedError("the training step implements the 'dot' attention")
+        self.mix, self.emb, self.att = mix_hidden_layer_3d, mix_speech_multiEmbedding, att_speech_layer
+        self.adj = adjust_layer if (adjust_layer is not None and config.is_SelfTune) else None
+        self.complex_mask = bool(config.is_ComlexMask)
+
+    def parameters(self):
+        mods = [self.mix, self.emb] + ([self.adj] if self.adj is not None else [])
+        out = []
+        for m in mods:
+            out += list(m.parameters())
+        return out
+
+    # ------------------------------------------------------------------------------ forward
+    def forward(self, mix_feas, spk_idx):
+        """-> ctx dict with masks and everything backward needs."""
+        lib = _lib.load()
+        B, T, F = mix_feas.shape
+        lin = self.mix.Linear
+        E = lin.out_features // F
+        saved = []
+        hidden = M.rnn_forward(self.mix._packed, mix_feas, save=saved)            # K2 + K3, gates saved
+        idx = self.emb.index_tensor(spk_idx)
+        table = self.emb.layer.weight
+        e = table.detach()[idx]                                                   # [B,S,EQ] gather (glue)
+        S, EQ = e.shape[1], e.shape[2]
+        hmean = None
+        if self.adj is not None:
+            hmean = hidden.mean(1)                                                # [B,2H]
+            cat = torch.cat([hmean.unsqueeze(1).expand(B, S, hmean.shape[1]), e], 2)
+            q = e + cat @ self.adj.layer.weight.detach().t()
+        else:
+            q = e
+        q = q.contiguous()
+        K = hidden.shape[2]
+        h2d = hidden.view(B * T, K)
+        if M.use_tensor_cores():
+            emb = M.linear_tc(M.split_bf16(h2d), M.weight_planes(lin.weight), lin.bias.detach(), B * T, F * E, K,
+                              act='tanh')
+        else:
+            emb = M.linear_fwd(h2d, lin.weight.detach(), lin.bias.detach(), 'tanh')
+        cplx = self.complex_mask
+        mode = _lib.ATT_DOT_CRM if cplx else _lib.ATT_DOT
+        masks = torch.empty((B, S, T, F, 2) if cplx else (B, S, T, F), device=hidden.device, dtype=torch.float32)
+        rc = lib.dl4ss_attn_dot_fwd(_lib.ptr(emb), T * F * E, _lib.ptr(q), B, S, T * F, E, mode,
+                                    float(config.cRM_k), float(config.cRM_C), _lib.ptr(masks), _lib.stream())
+        _lib.check(rc, 'dl4ss_attn_dot_fwd')
+        return {'B': B, 'T': T, 'F': F, 'E': E, 'S': S, 'EQ': EQ, 'saved': saved, 'hidden': hidden, 'idx': idx,
+                'e': e, 'hmean': hmean, 'q': q, 'emb': emb, 'masks': masks, 'x0': mix_feas}
+
+    # ------------------------------------------------------------------------------ loss + backward
+    def loss_and_grads(self, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, grad_scale=1.0):
+        """One forward + backward.  `global_batch`: utterances of the whole (all-rank) batch, so the
+        MSELoss means -- and therefore the summed gradients -- are those of the global batch.
+        Returns (loss, part0, part1) of THIS shard's contribution (sum over ranks = global loss)."""
+        lib = _lib.load()
+        with torch.no_grad():
+            ctx = self.forward(mix_feas, spk_idx)
+            B, T, F, E, S = ctx['B'], ctx['T'], ctx['F'], ctx['E'], ctx['S']
+            Bg = B if global_batch is None else int(global_batch)
+            cplx = self.complex_mask
+            masks = ctx['masks']
+            mix = mix_mag if cplx else mix_feas
+            kind = _lib.MASK_COMPLEX if cplx else _lib.MASK_REAL
+            acc = torch.zeros(2, device=masks.device, dtype=torch.float64)
+            rc = lib.dl4ss_mask_loss_fwd(_lib.ptr(masks), kind, _lib.ptr(mix, name='mix'), _lib.ptr(target, name='target'),
+                                         B, S, T * F, _lib.ptr(acc, torch.float64), _lib.stream())
+            _lib.check(rc, 'dl4ss_mask_loss_fwd')
+            n0 = float(Bg * S * T * F)
+            n1 = float(Bg * T * F)
+            if cplx:
+                l0, l1 = acc[0] / n0, acc[1] / n0
+                loss = l0 + l1
+                c0 = c1 = 2.0 * grad_scale / n0
+            else:
+                l0, l1 = acc[0] / n0, acc[1] / n1
+                loss = l0 + 0.5 * l1
+                c0, c1 = 2.0 * grad_scale / n0, grad_scale / n1
+            dmask = torch.empty_like(masks)
+            rc = lib.dl4ss_mask_loss_bwd(_lib.ptr(masks), kind, _lib.ptr(mix), _lib.ptr(target), B, S, T * F,
+                                         c0, c1, _lib.ptr(dmask), _lib.stream())
+            _lib.check(rc, 'dl4ss_mask_loss_bwd')
+            self.backward(ctx, dmask)
+        return loss, l0, l1
+
+    def backward(self, ctx, dmask):
+        lib = _lib.load()
+        B, T, F, E, S, EQ = ctx['B'], ctx['T'], ctx['F'], ctx['E'], ctx['S'], ctx['EQ']
+        cplx = self.complex_mask
+        mode = _lib.ATT_DOT_CRM if cplx else _lib.ATT_DOT
+        emb, q, masks, hidden = ctx['emb'], ctx['q'], ctx['masks'], ctx['hidden']
+        dq = torch.empty_like(q)
+        # attention + tanh backward: emb is overwritten by dz
+        rc = lib.dl4ss_attn_dot_bwd(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(masks), _lib.ptr(dmask), B, S, T * F, E, mode,
+                                    float(config.cRM_k), float(config.cRM_C), _lib.ptr(emb), _lib.ptr(dq), _lib.stream())
+        _lib.check(rc, 'dl4ss_attn_dot_bwd')
+        dz = emb.view(B * T, F * E)
+        lin = self.mix.Linear
+        h2d = hidden.view(B * T, -1)
+        _accum(lin.weight, dz.t() @ h2d)
+        _accum(lin.bias, dz.sum(0))
+        dh = (dz @ lin.weight.detach()).view(B, T, -1)
+        # speaker query backward (tiny: glue in torch)
+        table = self.emb.layer.weight
+        if self.adj is not None:
+            W = self.adj.layer.weight.detach()                                   # [EQ, C+EQ]
+            C = hidden.shape[2]
+            cat = torch.cat([ctx['hmean'].unsqueeze(1).expand(B, S, C), ctx['e']], 2)
+            _accum(self.adj.layer.weight, dq.reshape(B * S, EQ).t() @ cat.reshape(B * S, C + EQ))
+            dcat = dq @ W                                                        # [B,S,C+EQ]
+            de = dq + dcat[..., C:]
+            dh = dh + (dcat[..., :C].sum(1) / float(T)).unsqueeze(1)
+        else:
+            de = dq
+        gt = torch.zeros_like(table)
+        gt.index_add_(0, ctx['idx'].reshape(-1), de.reshape(B * S, EQ))
+        _accum(table, gt)
+        # encoder backward, top layer first
+        self.rnn_backward(ctx, dh.contiguous())
+
+    def rnn_backward(self, ctx, dy):
+        lib = _lib.load()
+        rnn = self.mix.layer
+        gru = isinstance(rnn, nn.GRU)
+        cell = _lib.CELL_GRU if gru else _lib.CELL_LSTM
+        G = 3 if gru else 4
+        H = rnn.hidden_size
+        B, T = ctx['B'], ctx['T']
+        dev = dy.device
+        layers = self.mix._packed.get()
+        for l in range(rnn.num_layers - 1, -1, -1):
+            sv, lw = ctx['saved'][l], layers[l]
+            whh = lw['whh']                                                      # [2,G*H,H]
+            dgx = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
+            dgh = torch.empty_like(dgx) if gru else None
+            carry = torch.empty(2, B, H, device=dev, dtype=torch.float32)
+            dg_cur = torch.empty(2, B, G * H, device=dev, dtype=torch.float32)
+            dh_rec = torch.empty(2, B, H, device=dev, dtype=torch.float32)
+            for s in range(T):
+                if s > 0:
+                    torch.bmm(dg_cur, whh, out=dh_rec)                           # per-step recurrent GEMM (cuBLAS)
+                rc = lib.dl4ss_rnn_bwd_step(cell, s, _lib.ptr(dy), _lib.ptr(dh_rec), _lib.ptr(sv['gates']),
+                                            _lib.ptr(sv['cells']), _lib.ptr(sv['y']), _lib.ptr(carry), _lib.ptr(dgx),
+                                            _lib.ptr(dgh), _lib.ptr(dg_cur), B, T, H, _lib.stream())
+                _lib.check(rc, 'dl4ss_rnn_bwd_step')
+            x2d = sv['x'].reshape(B * T, -1)
+            dgx2d = dgx.view(B * T, 2 * G * H)
+            dW_ih = dgx2d.t() @ x2d                                              # [2*G*H, in]
+            db_x = dgx2d.sum(0)
+            dgr = dgh if gru else dgx                                            # recurrent-side gate grads
+            y = sv['y']
+            for d, suf in enumerate(('', '_reverse')):
+                sl = slice(d * G * H, (d + 1) * G * H)
+                _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
+                _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
+                if d == 0:       # h_{t-1} of the forward direction is y[:, t-1, :H]
+                    dg_t, h_prev = dgr[:, 1:, 0, :], y[:, :-1, :H]
+                else:            # the reverse direction came from t+1
+                    dg_t, h_prev = dgr[:, :-1, 1, :], y[:, 1:, H:]
+                _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)),
+                       dg_t.reshape(-1, G * H).t() @ h_prev.reshape(-1, H))
+                _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
+            if l > 0:
+                dy = (dgx2d @ lw['wih']).view(B, T, -1).contiguous()
+
+    # ------------------------------------------------------------------------------ full step
+    def step(self, optimizer, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, group=None):
+        """zero_grad -> loss_and_grads -> all-reduce (if a process group is up) -> optimizer.step."""
+        optimizer.zero_grad(set_to_none=True)
+        out = self.loss_and_grads(mix_feas, spk_idx, target, mix_mag, global_batch)
+        allreduce_gradients(self.parameters(), group)
+        optimizer.step()
+        return out

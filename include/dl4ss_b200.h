@@ -146,7 +146,7 @@ int dl4ss_emb_attn_mask_fwd(const float *h, const float *W, const float *bias, c
 size_t dl4ss_split_bf16_bytes(long long R, int K);
 int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, void *stream);
 int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
-                        int ldc, int M, int N, int K, void *stream);
+                        int ldc, int M, int N, int K, int act, void *stream);
 int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
                                const float *q, int B, int T, int F, int E, int K, int S, int mode,
                                float crm_k, float crm_c, float *mask_out, void *stream);
@@ -178,6 +178,27 @@ int dl4ss_speaker_query_fwd(const float *h, int B, int T, int C, const float *ta
  * taken by the caller so shards of one global batch can be all-reduced first). */
 int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
                         int B, int S, int TF, double *loss_out, void *stream);
+
+/* ---- training step, backward side -----------------------------------------------------------
+ * loss = l0 + 0.5*l1 (real; EvalVer.py:641,659-666) or l_re + l_im (cRM; cRM_EvalVer.py:741-743).
+ * dl4ss_mask_loss_bwd: dmask = d(loss)/d(mask), same layout as mask.
+ *   real: c0 = 2*g/N0, c1 = g/N1 with N0 = B*S*T*F, N1 = B*T*F of the GLOBAL batch, g = upstream grad;
+ *   cRM : c0 = c1 = 2*g/N0.
+ * dl4ss_attn_dot_bwd: emb [B,TF,E] = tanh(z) ; q [B,S,E|2E] ; mask/dmask [B,S,TF(,2)] ->
+ *   dz [B,TF,E] = d(loss)/dz (may alias emb) and dq [B,S,E|2E] (zeroed by the callee).
+ * dl4ss_rnn_bwd_step: BPTT gate arithmetic of backward step s (s = 0 is the LAST forward step of each
+ *   direction).  dy [B,T,2H]; dh_rec [2,B,H] = dg_cur(previous call) x W_hh (host GEMM; unused at s = 0);
+ *   gates_save / cell_save / y from dl4ss_rnn_layer_*fwd; carry [2,B,H] state (LSTM dc, GRU dh*z);
+ *   dgx [B,T,2,G*H] = d/d(xproj) ; dgh (GRU only; NULL for LSTM) = d/d(W_hh h + b_hh) ;
+ *   dg_cur [2,B,G*H] = this step's recurrent-side gate gradients, contiguous for the next GEMM. */
+int dl4ss_mask_loss_bwd(const float *mask, int mask_kind, const float *mix, const float *target, int B,
+                        int S, int TF, float c0, float c1, float *dmask, void *stream);
+int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                       int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
+                       void *stream);
+int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, const float *gates_save,
+                       const float *cell_save, const float *y, float *carry, float *dgx, float *dgh,
+                       float *dg_cur, int B, int T, int H, void *stream);
 
 #ifdef __cplusplus
 }
