@@ -255,6 +255,83 @@ def run_reference(args):
     return 0
 
 
+def run_train(args):
+    """BASELINE configs[3]: one training step per 'step' (feature STFTs of mixture and clean sources, forward
+    with saved gates, MSE loss, hand-written backward, NCCL all-reduce of the flat gradient bucket, Adam),
+    utterances sharded by batch over the ranks (weak scaling: --train-batch per GPU)."""
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    else:
+        torch.cuda.set_device(0)
+    device = torch.device('cuda', local_rank if world > 1 else 0)
+    import dl4ss_b200 as d
+    d.load_library()
+    W, B = WORKLOAD, args.train_batch
+    sep = build_model(device)                       # same seed on every rank: identical replicas
+    step = d.TrainStep(sep.mix, sep.emb, sep.att, sep.adj)
+    opt = torch.optim.Adam([{'params': step.parameters()}], lr=2e-4)       # EvalVer.py:537-544
+    g = torch.Generator(device=device).manual_seed(11 + rank)
+    src = torch.randn(B, W['S'], W['L'], device=device, generator=g)
+    src = src / src.abs().amax(2, keepdim=True)
+    wav = src.sum(1).contiguous()
+    gi = torch.Generator().manual_seed(7 + rank)
+    idx = torch.sort(torch.stack([torch.randperm(W['num_spk'], generator=gi)[:W['S']] for _ in range(B)]), 1)[0].to(device)
+
+    def one_step():
+        batch = d.prepare_batch(wav, W['n_fft'], W['hop'], False, sources=src)          # K1: mixture + target STFTs
+        return step.step(opt, batch['mix_feas'], idx, batch['multi_spk_fea'].contiguous(), global_batch=B * world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        one_step()
+    barrier()
+    n0 = d.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank if world > 1 else 0)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step()[0]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = d.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    nparams = sum(p.numel() for p in step.parameters())
+    if rank == 0:
+        audio_s = world * B * W['L'] / SR * args.steps
+        cfg = workload_config(B)
+        cfg['workload'] = 'TDAA_beta 2-speaker training step (BASELINE configs[3]): STFT -> BLSTM attention masks -> MSE loss -> backward -> gradient all-reduce -> Adam'
+        cfg['allreduce_bytes_per_step'] = nparams * 4 if world > 1 else 0
+        print(json.dumps({'metric': 'training_audio_seconds_per_second', 'value': audio_s / (ms * 1e-3), 'unit': 'audio-s/s',
+                          'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic', 'config': cfg, 'gpu_launches': launches, 'clocks': clocks,
+                          'loss': float(loss), 'parameters': nparams}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def workload_config(B):
     W = WORKLOAD
     return {'workload': W['name'], 'batch_per_gpu': B, 'utterance_s': W['L'] / SR, 'sample_rate': SR,
@@ -274,9 +351,14 @@ def main():
     ap.add_argument('--ref-utts', type=int, default=8, help='utterances per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-utts', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="'train': BASELINE configs[3], STFT -> encoder -> masks -> loss -> backward -> all-reduce -> Adam")
+    ap.add_argument('--train-batch', type=int, default=64, help='utterances per GPU per training step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.mode == 'train':
+        return run_train(args)
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
