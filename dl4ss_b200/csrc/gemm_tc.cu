@@ -24,7 +24,8 @@ constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 2;
 constexpr int TA_BYTES = TBM * TBK * 2;                       // 16 KB
 constexpr int TB_BYTES = TBN * TBK * 2;                       // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                               // 2 per TMEM sub-partition: each takes half the columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ------------------------------------------------------------------------------------------ split
@@ -58,11 +59,11 @@ split_bf16_kernel(const float *__restrict__ x, int ld, long long R, int K, int K
 }
 
 // ------------------------------------------------------------------------------------------ epilogues
+template <int ACT>          // DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID, compile time: the epilogue is on the critical path
 struct EpiPlain {
     float *C;
     const float *bias;
     int ldc;
-    int act;             // DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID
 };
 struct EpiAttn {
     const float *bias;   // [F*E]
@@ -78,7 +79,7 @@ constexpr int ATT_BINS = TBN / ATT_EP;          // 4 frequency bins per N tile
 constexpr int ATT_SMAX = 4;                     // speakers per utterance handled in registers
 
 template <typename Epi> struct EpiTraits;
-template <> struct EpiTraits<EpiPlain> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; };
+template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; };
 template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS; static constexpr bool BINNED = true; };
 
 __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float crm_c) {
@@ -88,15 +89,18 @@ __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float c
 }
 
 // one accumulator row (this thread's TMEM lane) -> global
-__device__ __forceinline__ float apply_act(float x, int act) {
-    return act == DL4SS_ACT_TANH ? tanh_f(x) : act == DL4SS_ACT_SIGMOID ? sigmoid_f(x) : x;
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+    return ACT == DL4SS_ACT_TANH ? tanh_f(x) : ACT == DL4SS_ACT_SIGMOID ? sigmoid_f(x) : x;
 }
 
-__device__ __forceinline__ void epilogue_row(const EpiPlain &e, uint32_t taddr, int m, int n0, int M, int N) {
+// chalf: which half of the tile's columns this warp owns
+template <int ACT>
+__device__ __forceinline__ void epilogue_row(const EpiPlain<ACT> &e, uint32_t taddr, int m, int n0, int M, int N, int chalf) {
     float *crow = e.C + (size_t)m * e.ldc;
     const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
 #pragma unroll 1
-    for (int c = 0; c < TBN / 16; ++c) {
+    for (int c = chalf * (TBN / 32); c < (chalf + 1) * (TBN / 32); ++c) {
         float v[16];
         tmem_ld16(taddr + c * 16, v);          // warp-collective: executed by every lane
         if (m >= M) continue;
@@ -106,29 +110,29 @@ __device__ __forceinline__ void epilogue_row(const EpiPlain &e, uint32_t taddr, 
         for (int j = 0; j < 16; j += 4) {
             if (vec && n + j + 3 < N) {
                 float4 o;
-                o.x = apply_act(v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f), e.act);
-                o.y = apply_act(v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f), e.act);
-                o.z = apply_act(v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f), e.act);
-                o.w = apply_act(v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f), e.act);
+                o.x = apply_act<ACT>(v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f));
+                o.y = apply_act<ACT>(v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f));
+                o.z = apply_act<ACT>(v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f));
+                o.w = apply_act<ACT>(v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f));
                 *reinterpret_cast<float4 *>(crow + n + j) = o;
             } else {
 #pragma unroll
                 for (int jj = j; jj < j + 4; ++jj)
-                    if (n + jj < N) crow[n + jj] = apply_act(v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f), e.act);
+                    if (n + jj < N) crow[n + jj] = apply_act<ACT>(v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f));
             }
         }
     }
 }
 
 // n0 = first frequency bin of the tile; bin j of the tile sits in accumulator columns [64j, 64j+50)
-__device__ __forceinline__ void epilogue_row(const EpiAttn &e, uint32_t taddr, int m, int n0, int M, int N) {
+__device__ __forceinline__ void epilogue_row(const EpiAttn &e, uint32_t taddr, int m, int n0, int M, int N, int chalf) {
     const int EQ = e.crm ? 2 * ATT_E : ATT_E;
     const bool valid = m < M;
     const int mm = valid ? m : 0;
     const int b = mm / e.T, t = mm - b * e.T;
     const float *qb = e.q + (size_t)b * e.S * EQ;
 #pragma unroll 1
-    for (int bin = 0; bin < ATT_BINS; ++bin) {
+    for (int bin = chalf * (ATT_BINS / 2); bin < (chalf + 1) * (ATT_BINS / 2); ++bin) {
         const int f = n0 + bin;
         const bool fvalid = f < e.F;                      // warp-uniform
         const float *bias = e.bias + (size_t)(fvalid ? f : 0) * ATT_E;
@@ -190,7 +194,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -254,13 +258,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
     } else {
         const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
+        const int chalf = (warp - 2) >> 2;            // column half of the tile
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TBN;
-            epilogue_row(epi, taddr, m0 + quarter * 32 + lane, n0, M, N);
+            epilogue_row(epi, taddr, m0 + quarter * 32 + lane, n0, M, N, chalf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -369,8 +374,11 @@ extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, c
     DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "linear_tc_fwd: bad M/N/K/ldc %d/%d/%d/%d", M, N, K, ldc);
     if (M == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG(act >= DL4SS_ACT_NONE && act <= DL4SS_ACT_SIGMOID, "linear_tc_fwd: bad act %d", act);
-    EpiPlain e{C, bias, ldc, act};
-    return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), e, (cudaStream_t)stream);
+    if (act == DL4SS_ACT_TANH)
+        return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_TANH>{C, bias, ldc}, (cudaStream_t)stream);
+    if (act == DL4SS_ACT_SIGMOID)
+        return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_SIGMOID>{C, bias, ldc}, (cudaStream_t)stream);
+    return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream);
 }
 
 extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,

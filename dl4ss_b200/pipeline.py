@@ -70,6 +70,54 @@ class Separator(object):
     __call__ = separate
 
 
+class HostPipeline(object):
+    """Waveforms in pinned HOST memory -> separated waveforms in pinned HOST memory, with the H2D copy of
+    batch i+1 and the D2H copy of batch i-1 overlapped with the kernels of batch i (three streams, `depth`
+    device slots).  This is the call a user of the reference's eval loop makes per batch: the reference
+    moves features to the GPU and predictions back once per batch as well
+    (TDAA_beta/main_run_sstune_EvalVer.py:420 `.cuda()`, :60-61 `.data.cpu().numpy()`), serially.
+
+        pipe = HostPipeline(sep, B, L, S)
+        for h_wav, h_idx, h_out in batches: pipe.submit(h_wav, h_idx, h_out)
+        pipe.drain()            # all h_out buffers are complete after this
+    Each in-flight step needs its own h_out buffer (rotate >= depth of them)."""
+
+    def __init__(self, separator, B, L, S, depth=2, device=None):
+        self.sep = separator
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.depth = depth
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.d_wav = [torch.empty(B, L, device=dev, dtype=torch.float32) for _ in range(depth)]
+        self.d_idx = [torch.empty(B, S, device=dev, dtype=torch.int64) for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = torch.cuda.Event()
+        self.count = 0
+
+    def submit(self, h_wav, h_idx, h_out):
+        k = self.count % self.depth
+        self.count += 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_done[k])          # slot k's previous kernels have consumed d_wav[k]
+            self.d_wav[k].copy_(h_wav, non_blocking=True)
+            self.d_idx[k].copy_(h_idx, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        cur.wait_event(self.ev_in[k])
+        out = self.sep.separate(self.d_wav[k], self.d_idx[k], check_index=False)
+        self.ev_done[k].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done[k])
+            h_out.copy_(out, non_blocking=True)
+            out.record_stream(self.s_out)
+            self.ev_out.record(self.s_out)
+        return h_out
+
+    def drain(self):
+        """Make the current stream wait for every submitted D2H copy (then synchronize it to read h_out)."""
+        torch.cuda.current_stream().wait_event(self.ev_out)
+
+
 def mask_loss(masks, mix, target, complex_mask=None):
     """The reference's training/eval objective from masks (K5).
 
