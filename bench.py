@@ -125,6 +125,34 @@ def build_model(device):
     return d.Separator(mix, emb, att, adj, W['n_fft'], W['hop'])
 
 
+def kernel_stage_times(sep, wavs, idx, inner=8):
+    """STFT and mask+iSTFT stage times with the launch overhead amortised: `inner` back-to-back launches over
+    rotating input batches (4 x 41 MB of waveforms, fresh outputs: working set > 126 MB L2), CUDA events on
+    the launching stream.  These are the HBM-bound stages whose roofline the north star asks for."""
+    from dl4ss_b200 import features
+    W = WORKLOAD
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        batches = [sep.features(w) for w in wavs]
+        masks = torch.rand(wavs[0].shape[0], W['S'], batches[0]['mix_feas'].shape[1], batches[0]['mix_feas'].shape[2],
+                           device=wavs[0].device)
+        outs = {}
+        for name, fn in (('stft', lambda i: sep.features(wavs[i % len(wavs)])),
+                         ('mask_istft', lambda i: features.mask_istft(masks, batches[i % len(batches)]['mix_mag'], W['hop']))):
+            for i in range(2):
+                fn(i)
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = ev(), ev(); e0.record()
+                for i in range(inner):
+                    fn(i)
+                e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / inner)
+            outs[name] = best
+    return outs
+
+
 def stage_times(sep, wav, idx, reps=3):
     """Per-stage device time (CUDA events on the launching stream) of one step, for the roofline
     lines; run outside the timed region."""
@@ -444,6 +472,7 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         st = stage_times(sep, wavs[0], idx)
+        st.update(kernel_stage_times(sep, wavs, idx))
         alg = algorithmic(B)
         flops = {'rnn_xproj': alg['xproj_flops'], 'rnn_recurrent': alg['rec_flops'], 'emb_attn_mask': alg['emb_flops']}
         dom = max(flops, key=lambda k: st[k])

@@ -24,7 +24,8 @@ constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 2;
 constexpr int TA_BYTES = TBM * TBK * 2;                       // 16 KB
 constexpr int TB_BYTES = TBN * TBK * 2;                       // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
-constexpr int TC_EPI_WARPS = 8;                               // 2 per TMEM sub-partition: each takes half the columns
+constexpr int TC_EPI_WARPS = 16;                              // 4 per TMEM sub-partition: each takes a quarter of the columns
+constexpr int TC_EPI_PARTS = TC_EPI_WARPS / 4;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -79,8 +80,10 @@ constexpr int ATT_BINS = TBN / ATT_EP;          // 4 frequency bins per N tile
 constexpr int ATT_SMAX = 4;                     // speakers per utterance handled in registers
 
 template <typename Epi> struct EpiTraits;
-template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; };
-template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS; static constexpr bool BINNED = true; };
+// PARTS: epilogue warps per TMEM sub-partition (each takes 1/PARTS of the tile's columns).  The plain store
+// epilogue is bound by its row-strided stores and is fastest with 2, the attention epilogue is math bound: 4.
+template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; static constexpr int PARTS = 2; };
+template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS; static constexpr bool BINNED = true; static constexpr int PARTS = 4; };
 
 __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float crm_c) {
     float m = crm_k * tanhf(energy);
@@ -100,7 +103,7 @@ __device__ __forceinline__ void epilogue_row(const EpiPlain<ACT> &e, uint32_t ta
     float *crow = e.C + (size_t)m * e.ldc;
     const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
 #pragma unroll 1
-    for (int c = chalf * (TBN / 32); c < (chalf + 1) * (TBN / 32); ++c) {
+    for (int c = chalf * (TBN / 16 / EpiTraits<EpiPlain<ACT>>::PARTS); c < (chalf + 1) * (TBN / 16 / EpiTraits<EpiPlain<ACT>>::PARTS); ++c) {
         float v[16];
         tmem_ld16(taddr + c * 16, v);          // warp-collective: executed by every lane
         if (m >= M) continue;
@@ -132,7 +135,7 @@ __device__ __forceinline__ void epilogue_row(const EpiAttn &e, uint32_t taddr, i
     const int b = mm / e.T, t = mm - b * e.T;
     const float *qb = e.q + (size_t)b * e.S * EQ;
 #pragma unroll 1
-    for (int bin = chalf * (ATT_BINS / 2); bin < (chalf + 1) * (ATT_BINS / 2); ++bin) {
+    for (int bin = chalf * (ATT_BINS / EpiTraits<EpiAttn>::PARTS); bin < (chalf + 1) * (ATT_BINS / EpiTraits<EpiAttn>::PARTS); ++bin) {
         const int f = n0 + bin;
         const bool fvalid = f < e.F;                      // warp-uniform
         const float *bias = e.bias + (size_t)(fvalid ? f : 0) * ATT_E;
@@ -194,7 +197,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TC_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EpiTraits<Epi>::PARTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -256,9 +259,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else {
+    } else if (((warp - 2) >> 2) < EpiTraits<Epi>::PARTS) {
         const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
-        const int chalf = (warp - 2) >> 2;            // column half of the tile
+        const int chalf = (warp - 2) >> 2;            // column part of the tile
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;

@@ -41,11 +41,37 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
         const WavT *w = wav + (size_t)b * L;
         const int s0 = t0 * hop - NFFT / 2;
         const int ns = (nf - 1) * hop + NFFT;
-        for (int i = tid; i < ns; i += STFT_THREADS) {
-            int j = s0 + i;
-            j = (j < 0) ? -j : j;
-            j = (j >= L) ? 2 * (L - 1) - j : j;
-            samples[i] = (float)w[j];
+        bool fast = false;
+        if constexpr (sizeof(WavT) == 4) {
+            // interior tile, 16-byte aligned: all loads of a thread are issued before the first store
+            // (the scalar loop below stalls on every LDG -> STS pair: 41 % of the kernel's stall samples)
+            fast = (s0 >= 0) && (s0 + ns <= L) && ((ns & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(w + s0) & 15) == 0);
+            if (fast) {
+                const float4 *src = reinterpret_cast<const float4 *>(w + s0);
+                float4 *dst = reinterpret_cast<float4 *>(samples);
+                const int n4 = ns >> 2;
+                constexpr int MAXV = ((STFT_FT - 1) * NFFT + NFFT) / 4 / STFT_THREADS + 1;   // hop <= 256
+                float4 r[MAXV];
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const int i = tid + k * STFT_THREADS;
+                    if (i < n4) r[k] = __ldg(src + i);
+                }
+#pragma unroll
+                for (int k = 0; k < MAXV; ++k) {
+                    const int i = tid + k * STFT_THREADS;
+                    if (i < n4) dst[i] = r[k];
+                }
+            }
+        }
+        if (!fast) {
+            for (int i = tid; i < ns; i += STFT_THREADS) {
+                int j = s0 + i;
+                j = (j < 0) ? -j : j;
+                j = (j >= L) ? 2 * (L - 1) - j : j;
+                samples[i] = (float)w[j];
+            }
         }
     }
     __syncthreads();
@@ -134,7 +160,8 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     float2 *tw = reinterpret_cast<float2 *>(smem_raw);
     float2 *xch = tw + 256;
     float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);
-    float *ybuf = win + NFFT;                                          // max_frames*S*256
+    float *wsq = win + NFFT;                                           // 256: window^2 (un-normalised taps)
+    float *ybuf = wsq + NFFT;                                          // max_frames*S*256
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / tiles_per_utt;
@@ -151,7 +178,11 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     const int npairs = (nitems + 1) >> 1;
 
     fill_twiddles(tw, tid, STFT_THREADS);
-    win[tid] = window[tid] * (1.0f / NFFT);     // fold the 1/N of the inverse transform
+    {
+        const float wt = window[tid];
+        win[tid] = wt * (1.0f / NFFT);          // fold the 1/N of the inverse transform
+        wsq[tid] = wt * wt;
+    }
     __syncthreads();
 
     const int g = tid >> 4, l16 = tid & 15;
@@ -253,21 +284,43 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
 
     // overlap-add + window-sum-square normalisation + trim
     const int span = m_hi - m_lo;
-    const float wscale = (float)NFFT * (float)NFFT;    // win[] carries 1/N
-    for (int s = 0; s < S; ++s) {
-        float *o = out + ((size_t)b * S + s) * Lout + (m_lo - NFFT / 2);
-        for (int i = tid; i < span; i += STFT_THREADS) {
+    if ((hop & 3) == 0) {
+        // 4 consecutive samples share their frame set (hop % 4 == 0): float4 smem reads, one float4 store
+        const int span4 = span >> 2;          // span = blocks*hop is a multiple of 4
+        for (int idx = tid; idx < S * span4; idx += STFT_THREADS) {
+            const int s = idx / span4;
+            const int i = (idx - s * span4) << 2;
             const int m = m_lo + i;
-            int t1 = min(t_hi, m / hop);
-            float acc = 0.f, env = 0.f;
+            const int t1 = min(t_hi, m / hop);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = acc;
             for (int t = t1; t >= t_lo && m - t * hop < NFFT; --t) {
                 const int n = m - t * hop;
-                acc += ybuf[(size_t)((t - t_lo) * S + s) * NFFT + n];
-                const float w = win[n];
-                env = fmaf(w, w, env);
+                const float4 yv = *reinterpret_cast<const float4 *>(ybuf + (size_t)((t - t_lo) * S + s) * NFFT + n);
+                const float4 wv = *reinterpret_cast<const float4 *>(wsq + n);
+                acc.x += yv.x; acc.y += yv.y; acc.z += yv.z; acc.w += yv.w;
+                env.x += wv.x; env.y += wv.y; env.z += wv.z; env.w += wv.w;
             }
-            env *= wscale;
-            o[i] = (env > 1.17549435e-38f) ? acc / env : acc;
+            float4 o4;
+            o4.x = (env.x > 1.17549435e-38f) ? acc.x / env.x : acc.x;
+            o4.y = (env.y > 1.17549435e-38f) ? acc.y / env.y : acc.y;
+            o4.z = (env.z > 1.17549435e-38f) ? acc.z / env.z : acc.z;
+            o4.w = (env.w > 1.17549435e-38f) ? acc.w / env.w : acc.w;
+            *reinterpret_cast<float4 *>(out + ((size_t)b * S + s) * Lout + (m_lo - NFFT / 2) + i) = o4;
+        }
+    } else {
+        for (int s = 0; s < S; ++s) {
+            float *o = out + ((size_t)b * S + s) * Lout + (m_lo - NFFT / 2);
+            for (int i = tid; i < span; i += STFT_THREADS) {
+                const int m = m_lo + i;
+                int t1 = min(t_hi, m / hop);
+                float acc = 0.f, env = 0.f;
+                for (int t = t1; t >= t_lo && m - t * hop < NFFT; --t) {
+                    const int n = m - t * hop;
+                    acc += ybuf[(size_t)((t - t_lo) * S + s) * NFFT + n];
+                    env += wsq[n];
+                }
+                o[i] = (env > 1.17549435e-38f) ? acc / env : acc;
+            }
         }
     }
 }
@@ -335,7 +388,7 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
     bpt = cdiv(nblocks, tiles);
     const int max_frames = bpt + halo + 1;
     const size_t smem = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                        NFFT * sizeof(float) + (size_t)max_frames * S * NFFT * sizeof(float);
+                        2 * NFFT * sizeof(float) + (size_t)max_frames * S * NFFT * sizeof(float);
     if (smem > 220 * 1024) {
         set_error("mask_istft: S=%d hop=%d needs %zu B of shared memory", S, hop, smem);
         return DL4SS_EUNSUPPORTED;
