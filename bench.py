@@ -126,27 +126,40 @@ def build_model(device):
 
 
 def kernel_stage_times(sep, wavs, idx, inner=8):
-    """STFT and mask+iSTFT stage times with the launch overhead amortised: `inner` back-to-back launches over
-    rotating input batches (4 x 41 MB of waveforms, fresh outputs: working set > 126 MB L2), CUDA events on
-    the launching stream.  These are the HBM-bound stages whose roofline the north star asks for."""
+    """STFT and mask+iSTFT kernel times without host launch overhead: `inner` launches over rotating input
+    batches (4 x 41 MB of waveforms / 4 x 82 MB of spectra: working set > 126 MB L2) captured in a CUDA graph
+    and replayed; CUDA events on the replaying stream.  These are the HBM-bound stages whose roofline the
+    north star asks for; their kernels run ~50-100 us, the same order as a Python-side launch."""
     from dl4ss_b200 import features
     W = WORKLOAD
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    outs = {}
     with torch.no_grad():
         batches = [sep.features(w) for w in wavs]
-        masks = torch.rand(wavs[0].shape[0], W['S'], batches[0]['mix_feas'].shape[1], batches[0]['mix_feas'].shape[2],
-                           device=wavs[0].device)
-        outs = {}
-        for name, fn in (('stft', lambda i: sep.features(wavs[i % len(wavs)])),
-                         ('mask_istft', lambda i: features.mask_istft(masks, batches[i % len(batches)]['mix_mag'], W['hop']))):
+        B, T, F = batches[0]['mix_feas'].shape
+        masks = torch.rand(B, W['S'], T, F, device=wavs[0].device)
+        o_feat = [torch.empty_like(batches[0]['mix_feas']) for _ in range(2)]
+        o_cplx = [torch.empty_like(batches[0]['mix_mag']) for _ in range(2)]
+        o_wav = [torch.empty(B, W['S'], W['hop'] * (T - 1), device=wavs[0].device) for _ in range(2)]
+        fns = {'stft': lambda i: features.stft_features(wavs[i % len(wavs)], W['n_fft'], W['hop'], 'hann', 'abs',
+                                                        out_feat=o_feat[i % 2], out_cplx=o_cplx[i % 2]),
+               'mask_istft': lambda i: features.mask_istft(masks, batches[i % len(batches)]['mix_mag'], W['hop'],
+                                                           out=o_wav[i % 2])}
+        for name, fn in fns.items():
             for i in range(2):
                 fn(i)
             torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    for i in range(inner):
+                        fn(i)
+            torch.cuda.synchronize()
             best = 1e9
-            for _ in range(3):
+            for _ in range(5):
                 e0, e1 = ev(), ev(); e0.record()
-                for i in range(inner):
-                    fn(i)
+                graph.replay()
                 e1.record(); torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / inner)
             outs[name] = best

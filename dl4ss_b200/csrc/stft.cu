@@ -14,27 +14,51 @@ constexpr int STFT_GROUPS = STFT_THREADS / 16;   // 16-lane FFT groups per CTA
 constexpr int STFT_FT = 2 * STFT_GROUPS;         // frames per tile (two per group)
 constexpr int NFFT = 256;
 constexpr int NBIN = 129;
+// K1 runs 128-thread CTAs (16 frames per tile): 8 CTAs per SM in different phases overlap one CTA's staging
+// loads with the others' FFTs, and the last wave is finer grained
+constexpr int K1_THREADS = 128;
+constexpr int K1_GROUPS = K1_THREADS / 16;
+constexpr int K1_FT = 2 * K1_GROUPS;
+
+// exp(-2*pi*i*n1*k2/256) laid out [k2][n1] (fft256.cuh), built once per device
+__device__ float2 g_tw256[256];
+__global__ void init_twiddles_kernel() { fill_twiddles(g_tw256, threadIdx.x, blockDim.x); }
+
+static int ensure_twiddles(cudaStream_t st) {
+    static bool done[64] = {false};
+    int dev = 0;
+    DL4SS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (!done[dev] || dev == 63) {
+        init_twiddles_kernel<<<1, 256, 0, st>>>();
+        DL4SS_LAUNCH_CHECK("init_twiddles_kernel");
+        done[dev] = true;
+    }
+    return DL4SS_OK;
+}
 
 // ------------------------------------------------------------------------------------ K1
 template <typename WavT>
-__global__ void __launch_bounds__(STFT_THREADS)
+__global__ void __launch_bounds__(K1_THREADS)
 stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt,
                const float *__restrict__ window, int feat_mode, float eps, int conj,
                float *__restrict__ feat, float2 *__restrict__ cplx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tw = reinterpret_cast<float2 *>(smem_raw);                 // 256 float2
     float2 *xch = tw + 256;                                            // groups * 272 float2
-    float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);   // 256
+    float *win = reinterpret_cast<float *>(xch + K1_GROUPS * DL4SS_XCH_FLOAT2);   // 256
     float *samples = win + NFFT;                                       // (FT-1)*hop + 256
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / tiles_per_utt;
     const int tile = blockIdx.x - b * tiles_per_utt;
-    const int t0 = tile * STFT_FT;
-    const int nf = min(STFT_FT, T - t0);
+    const int t0 = tile * K1_FT;
+    const int nf = min(K1_FT, T - t0);
 
-    fill_twiddles(tw, tid, STFT_THREADS);
-    win[tid] = window[tid];
+    for (int i = tid; i < NFFT; i += K1_THREADS) {
+        tw[i] = g_tw256[i];
+        win[i] = window[i];
+    }
 
     // stage the tile's samples once: frame t spans signal [t*hop-128, t*hop+128), reflect-padded
     {
@@ -51,22 +75,22 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
                 const float4 *src = reinterpret_cast<const float4 *>(w + s0);
                 float4 *dst = reinterpret_cast<float4 *>(samples);
                 const int n4 = ns >> 2;
-                constexpr int MAXV = ((STFT_FT - 1) * NFFT + NFFT) / 4 / STFT_THREADS + 1;   // hop <= 256
+                constexpr int MAXV = ((K1_FT - 1) * NFFT + NFFT) / 4 / K1_THREADS + 1;   // hop <= 256
                 float4 r[MAXV];
 #pragma unroll
                 for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * STFT_THREADS;
+                    const int i = tid + k * K1_THREADS;
                     if (i < n4) r[k] = __ldg(src + i);
                 }
 #pragma unroll
                 for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * STFT_THREADS;
+                    const int i = tid + k * K1_THREADS;
                     if (i < n4) dst[i] = r[k];
                 }
             }
         }
         if (!fast) {
-            for (int i = tid; i < ns; i += STFT_THREADS) {
+            for (int i = tid; i < ns; i += K1_THREADS) {
                 int j = s0 + i;
                 j = (j < 0) ? -j : j;
                 j = (j >= L) ? 2 * (L - 1) - j : j;
@@ -161,7 +185,8 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     float2 *xch = tw + 256;
     float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);
     float *wsq = win + NFFT;                                           // 256: window^2 (un-normalised taps)
-    float *ybuf = wsq + NFFT;                                          // max_frames*S*256
+    float *inv_full = wsq + NFFT;                                      // 256: 1/sum of window^2 over a full frame set
+    float *ybuf = inv_full + NFFT;                                          // max_frames*S*256
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / tiles_per_utt;
@@ -177,7 +202,7 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     const int nitems = nfr * S;
     const int npairs = (nitems + 1) >> 1;
 
-    fill_twiddles(tw, tid, STFT_THREADS);
+    tw[tid] = g_tw256[tid];
     {
         const float wt = window[tid];
         win[tid] = wt * (1.0f / NFFT);          // fold the 1/N of the inverse transform
@@ -284,7 +309,51 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
 
     // overlap-add + window-sum-square normalisation + trim
     const int span = m_hi - m_lo;
-    if ((hop & 3) == 0) {
+    const int hop_shift = ((hop & (hop - 1)) == 0 && hop >= 4) ? (31 - __clz(hop)) : -1;
+    if (hop_shift >= 0) {
+        // power-of-two hop (64 / 128 in every reference config): R = 256/hop frames cover every interior
+        // sample; their window^2 sum depends only on m mod hop -> reciprocal table, no divisions
+        const int R = NFFT >> hop_shift;
+        if (tid < hop) {          // wsq is visible: written before the __syncthreads above
+            float e = 0.f;
+            for (int r = 0; r < R; ++r) e += wsq[tid + (r << hop_shift)];
+            inv_full[tid] = (e > 1.17549435e-38f) ? 1.0f / e : 1.0f;
+        }
+        __syncthreads();
+        const int span4 = span >> 2;
+        for (int s = 0; s < S; ++s) {
+            float *o = out + ((size_t)b * S + s) * Lout + (m_lo - NFFT / 2);
+            for (int i4 = tid; i4 < span4; i4 += STFT_THREADS) {
+                const int m = m_lo + (i4 << 2);
+                const int t1 = m >> hop_shift;
+                const int n0 = m - (t1 << hop_shift);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t1 <= t_hi && t1 - (R - 1) >= t_lo) {
+                    for (int r = 0; r < R; ++r) {
+                        const float4 yv = *reinterpret_cast<const float4 *>(
+                            ybuf + (size_t)((t1 - r - t_lo) * S + s) * NFFT + n0 + (r << hop_shift));
+                        acc.x += yv.x; acc.y += yv.y; acc.z += yv.z; acc.w += yv.w;
+                    }
+                    const float4 iv = *reinterpret_cast<const float4 *>(inv_full + n0);
+                    acc.x *= iv.x; acc.y *= iv.y; acc.z *= iv.z; acc.w *= iv.w;
+                } else {          // utterance edges: partial frame set
+                    float4 env = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int t = min(t_hi, t1); t >= t_lo && m - (t << hop_shift) < NFFT; --t) {
+                        const int n = m - (t << hop_shift);
+                        const float4 yv = *reinterpret_cast<const float4 *>(ybuf + (size_t)((t - t_lo) * S + s) * NFFT + n);
+                        const float4 wv = *reinterpret_cast<const float4 *>(wsq + n);
+                        acc.x += yv.x; acc.y += yv.y; acc.z += yv.z; acc.w += yv.w;
+                        env.x += wv.x; env.y += wv.y; env.z += wv.z; env.w += wv.w;
+                    }
+                    acc.x = (env.x > 1.17549435e-38f) ? acc.x / env.x : acc.x;
+                    acc.y = (env.y > 1.17549435e-38f) ? acc.y / env.y : acc.y;
+                    acc.z = (env.z > 1.17549435e-38f) ? acc.z / env.z : acc.z;
+                    acc.w = (env.w > 1.17549435e-38f) ? acc.w / env.w : acc.w;
+                }
+                *reinterpret_cast<float4 *>(o + (i4 << 2)) = acc;
+            }
+        }
+    } else if ((hop & 3) == 0) {
         // 4 consecutive samples share their frame set (hop % 4 == 0): float4 smem reads, one float4 store
         const int span4 = span >> 2;          // span = blocks*hop is a multiple of 4
         for (int idx = tid; idx < S * span4; idx += STFT_THREADS) {
@@ -345,19 +414,20 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
     }
     if (B == 0) return DL4SS_OK;
     const int T = 1 + L / hop;
-    const int tiles = cdiv(T, STFT_FT);
-    const size_t smem = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                        NFFT * sizeof(float) + ((STFT_FT - 1) * (size_t)hop + NFFT) * sizeof(float);
+    const int tiles = cdiv(T, K1_FT);
+    const size_t smem = 256 * sizeof(float2) + K1_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
+                        NFFT * sizeof(float) + ((K1_FT - 1) * (size_t)hop + NFFT) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    { int rc = ensure_twiddles(st); if (rc) return rc; }
     const long long grid = (long long)B * tiles;
     DL4SS_CHECK_ARG(grid < (1ll << 31), "stft_feat: grid too large");
     if (wav_dtype == DL4SS_WAV_F32) {
         DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stft256_kernel<float><<<(unsigned)grid, STFT_THREADS, smem, st>>>(
+        stft256_kernel<float><<<(unsigned)grid, K1_THREADS, smem, st>>>(
             (const float *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
     } else {
         DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stft256_kernel<double><<<(unsigned)grid, STFT_THREADS, smem, st>>>(
+        stft256_kernel<double><<<(unsigned)grid, K1_THREADS, smem, st>>>(
             (const double *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
     }
     DL4SS_LAUNCH_CHECK("stft256_kernel");
@@ -388,12 +458,13 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
     bpt = cdiv(nblocks, tiles);
     const int max_frames = bpt + halo + 1;
     const size_t smem = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                        2 * NFFT * sizeof(float) + (size_t)max_frames * S * NFFT * sizeof(float);
+                        3 * NFFT * sizeof(float) + (size_t)max_frames * S * NFFT * sizeof(float);
     if (smem > 220 * 1024) {
         set_error("mask_istft: S=%d hop=%d needs %zu B of shared memory", S, hop, smem);
         return DL4SS_EUNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    { int rc = ensure_twiddles(st); if (rc) return rc; }
     const long long grid = (long long)B * tiles;
     DL4SS_CHECK_ARG(grid < (1ll << 31), "mask_istft: grid too large");
 #define LAUNCH_ISTFT(KIND)                                                                             \

@@ -324,3 +324,30 @@ def test_end_to_end_crm(cuda):
     lref = mr.loss_ref(ref['cfg'], r, y)
     l, _, _ = d.mask_loss(out['masks'], out['mix_mag'], y.to(cuda))
     assert abs(l.item() - lref[0].item()) < 1e-4 * abs(lref[0].item())
+
+
+def test_baseline_config0_shape_hop64(cuda):
+    """BASELINE configs[0] at full size: 8 kHz, 256-pt STFT hop 64, BLSTM 2x300, batch 8 synthetic 4 s mixtures,
+    2 speakers -- waveforms -> separated waveforms against the CPU oracle (the reference's CPU-runnable case)."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr, stft_ref as sr, synth
+    B, L, S, hop = 8, 32000, 2, 64
+    batch = synth.make_batch(B, L, S, seed=9)
+    T = 1 + L // hop
+    assert T == 501
+    ref, ours = build_pair('lstm', 2, 129, T, False)
+    feats = [sr.features_ref(w, 256, hop) for w in batch['mix_wav']]
+    feas = torch.from_numpy(np.stack([f['mix_feas'] for f in feats]))
+    phase = np.stack([f['mix_phase'] for f in feats])
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, batch['spk_idx'])
+    wav_ref = mr.reconstruct_ref(r, phase, hop)
+    d.config.FRAME_SHIFT = hop
+    try:
+        sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'], hop=hop)
+        out = sep.separate(torch.from_numpy(batch['mix_wav']).to(cuda), batch['spk_idx'], return_all=True)
+    finally:
+        d.config.FRAME_SHIFT = 128
+    assert tuple(out['wav'].shape) == (B, S, hop * (T - 1))
+    assert (out['masks'].cpu() - r['masks']).abs().max().item() < TOL
+    assert rel_err(out['wav'].cpu().numpy(), wav_ref) < TOL
