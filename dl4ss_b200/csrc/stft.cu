@@ -38,16 +38,22 @@ static int ensure_twiddles(cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------ K1
-template <typename WavT>
+__device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT-class, max relative error 2^-23
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// FEAT / CPLX are compile time: the output loop is a third of the kernel's instructions
+template <typename WavT, int FEAT, bool CPLX>
 __global__ void __launch_bounds__(K1_THREADS)
 stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt,
-               const float *__restrict__ window, int feat_mode, float eps, int conj,
+               const float *__restrict__ window, float eps, int conj,
                float *__restrict__ feat, float2 *__restrict__ cplx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tw = reinterpret_cast<float2 *>(smem_raw);                 // 256 float2
     float2 *xch = tw + 256;                                            // groups * 272 float2
     float *win = reinterpret_cast<float *>(xch + K1_GROUPS * DL4SS_XCH_FLOAT2);   // 256
-    float *samples = win + NFFT;                                       // (FT-1)*hop + 256
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / tiles_per_utt;
@@ -60,58 +66,50 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
         win[i] = window[i];
     }
 
-    // stage the tile's samples once: frame t spans signal [t*hop-128, t*hop+128), reflect-padded
-    {
-        const WavT *w = wav + (size_t)b * L;
-        const int s0 = t0 * hop - NFFT / 2;
-        const int ns = (nf - 1) * hop + NFFT;
-        bool fast = false;
-        if constexpr (sizeof(WavT) == 4) {
-            // interior tile, 16-byte aligned: all loads of a thread are issued before the first store
-            // (the scalar loop below stalls on every LDG -> STS pair: 41 % of the kernel's stall samples)
-            fast = (s0 >= 0) && (s0 + ns <= L) && ((ns & 3) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(w + s0) & 15) == 0);
-            if (fast) {
-                const float4 *src = reinterpret_cast<const float4 *>(w + s0);
-                float4 *dst = reinterpret_cast<float4 *>(samples);
-                const int n4 = ns >> 2;
-                constexpr int MAXV = ((K1_FT - 1) * NFFT + NFFT) / 4 / K1_THREADS + 1;   // hop <= 256
-                float4 r[MAXV];
-#pragma unroll
-                for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * K1_THREADS;
-                    if (i < n4) r[k] = __ldg(src + i);
-                }
-#pragma unroll
-                for (int k = 0; k < MAXV; ++k) {
-                    const int i = tid + k * K1_THREADS;
-                    if (i < n4) dst[i] = r[k];
-                }
-            }
-        }
-        if (!fast) {
-            for (int i = tid; i < ns; i += K1_THREADS) {
-                int j = s0 + i;
-                j = (j < 0) ? -j : j;
-                j = (j >= L) ? 2 * (L - 1) - j : j;
-                samples[i] = (float)w[j];
-            }
-        }
-    }
-    __syncthreads();
+    __syncthreads();                       // twiddle / window tables: the kernel's only CTA-wide sync
 
     const int g = tid >> 4, l16 = tid & 15;
     const int fa = 2 * g, fb = 2 * g + 1;
     const bool va = fa < nf, vb = fb < nf;
 
+    // Every 16-lane group pulls its two frames straight from global memory (64-byte coalesced rows per n2;
+    // frame t spans signal [t*hop-128, t*hop+128), reflect-padded at the utterance edges).  The 50-75 % overlap
+    // between neighbouring frames is served by L1/L2 (DRAM still sees each sample once), and without a
+    // staging phase the warps of a CTA never wait on each other.
     float2 v[16];
     {
-        const float *sa = samples + (va ? fa : 0) * hop + l16;
-        const float *sb = samples + (vb ? fb : 0) * hop + l16;
+        const WavT *w = wav + (size_t)b * L;
+        float xa[16], xb[16];
+        const int sa0 = (t0 + (va ? fa : 0)) * hop - NFFT / 2;
+        const int sb0 = (t0 + (vb ? fb : 0)) * hop - NFFT / 2;
+        if (sa0 >= 0 && sa0 + NFFT <= L) {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) xa[n2] = (float)w[sa0 + l16 + 16 * n2];
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                int j = sa0 + l16 + 16 * n2;
+                j = (j < 0) ? -j : j;
+                j = (j >= L) ? 2 * (L - 1) - j : j;
+                xa[n2] = (float)w[j];
+            }
+        }
+        if (sb0 >= 0 && sb0 + NFFT <= L) {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) xb[n2] = (float)w[sb0 + l16 + 16 * n2];
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                int j = sb0 + l16 + 16 * n2;
+                j = (j < 0) ? -j : j;
+                j = (j >= L) ? 2 * (L - 1) - j : j;
+                xb[n2] = (float)w[j];
+            }
+        }
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) {
-            float w = win[l16 + 16 * n2];
-            v[n2] = make_float2(sa[16 * n2] * w, sb[16 * n2] * w);
+            const float wv = win[l16 + 16 * n2];
+            v[n2] = make_float2(xa[n2] * wv, xb[n2] * wv);
         }
     }
     fft256_group<false>(v, l16, xch + g * DL4SS_XCH_FLOAT2, tw);
@@ -120,8 +118,9 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
     //   XA[k] = (Z[k] + conj(Z[256-k]))/2 ,  XB[k] = (Z[k] - conj(Z[256-k]))/(2i)
     // lane holds Z[16*k1+l16] in v[k1]; Z[256-k] lives in lane (16-l16)&15, register 15-k1
     // (lane 0: own register (16-k1)&15).
-    const size_t rowa = ((size_t)b * T + t0 + fa) * NBIN;
-    const size_t rowb = rowa + NBIN;
+    const size_t rowa = ((size_t)b * T + t0 + fa) * NBIN + l16;
+    float *fpa = feat + rowa, *fpb = fpa + NBIN;
+    float2 *cpa = cplx + rowa, *cpb = cpa + NBIN;
     const int src = (16 - l16) & 15;
     const float sgn = conj ? -1.0f : 1.0f;
 #pragma unroll
@@ -135,36 +134,35 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
         }
         float2 xa = make_float2(0.5f * (z.x + px), 0.5f * (z.y - py));
         float2 xb = make_float2(0.5f * (z.y + py), -0.5f * (z.x - px));
-        const int k = 16 * k1 + l16;
-        if (feat_mode != DL4SS_FEAT_NONE) {
-            float ma = sqrtf(fmaf(xa.x, xa.x, xa.y * xa.y));
-            float mb = sqrtf(fmaf(xb.x, xb.x, xb.y * xb.y));
-            if (feat_mode == DL4SS_FEAT_LOG) {
+        if (FEAT != DL4SS_FEAT_NONE) {
+            float ma = sqrt_approx(fmaf(xa.x, xa.x, xa.y * xa.y));
+            float mb = sqrt_approx(fmaf(xb.x, xb.x, xb.y * xb.y));
+            if (FEAT == DL4SS_FEAT_LOG) {
                 ma = logf(ma + eps);
                 mb = logf(mb + eps);
             }
-            if (va) feat[rowa + k] = ma;
-            if (vb) feat[rowb + k] = mb;
+            if (va) fpa[16 * k1] = ma;
+            if (vb) fpb[16 * k1] = mb;
         }
-        if (cplx != nullptr) {
-            if (va) cplx[rowa + k] = make_float2(xa.x, sgn * xa.y);
-            if (vb) cplx[rowb + k] = make_float2(xb.x, sgn * xb.y);
+        if (CPLX) {
+            if (va) cpa[16 * k1] = make_float2(xa.x, sgn * xa.y);
+            if (vb) cpb[16 * k1] = make_float2(xb.x, sgn * xb.y);
         }
     }
     if (l16 == 0) {   // Nyquist bin: Z[128] = XA[128] + i*XB[128], both real
         float xa = v[8].x, xb = v[8].y;
-        if (feat_mode != DL4SS_FEAT_NONE) {
+        if (FEAT != DL4SS_FEAT_NONE) {
             float ma = fabsf(xa), mb = fabsf(xb);
-            if (feat_mode == DL4SS_FEAT_LOG) {
+            if (FEAT == DL4SS_FEAT_LOG) {
                 ma = logf(ma + eps);
                 mb = logf(mb + eps);
             }
-            if (va) feat[rowa + 128] = ma;
-            if (vb) feat[rowb + 128] = mb;
+            if (va) fpa[128] = ma;
+            if (vb) fpb[128] = mb;
         }
-        if (cplx != nullptr) {
-            if (va) cplx[rowa + 128] = make_float2(xa, 0.0f);
-            if (vb) cplx[rowb + 128] = make_float2(xb, 0.0f);
+        if (CPLX) {
+            if (va) cpa[128] = make_float2(xa, 0.0f);
+            if (vb) cpb[128] = make_float2(xb, 0.0f);
         }
     }
 }
@@ -416,20 +414,32 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
     const int T = 1 + L / hop;
     const int tiles = cdiv(T, K1_FT);
     const size_t smem = 256 * sizeof(float2) + K1_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                        NFFT * sizeof(float) + ((K1_FT - 1) * (size_t)hop + NFFT) * sizeof(float);
+                        NFFT * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     { int rc = ensure_twiddles(st); if (rc) return rc; }
     const long long grid = (long long)B * tiles;
     DL4SS_CHECK_ARG(grid < (1ll << 31), "stft_feat: grid too large");
-    if (wav_dtype == DL4SS_WAV_F32) {
-        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stft256_kernel<float><<<(unsigned)grid, K1_THREADS, smem, st>>>(
-            (const float *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
-    } else {
-        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stft256_kernel<double><<<(unsigned)grid, K1_THREADS, smem, st>>>(
-            (const double *)wav, L, hop, T, tiles, window, feat_mode, eps, conj, feat_out, (float2 *)cplx_out);
-    }
+#define LAUNCH_K1(WT, FM, CP)                                                                                  \
+    do {                                                                                                        \
+        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        stft256_kernel<WT, FM, CP><<<(unsigned)grid, K1_THREADS, smem, st>>>(                                   \
+            (const WT *)wav, L, hop, T, tiles, window, eps, conj, feat_out, (float2 *)cplx_out);                \
+    } while (0)
+#define DISPATCH_K1(WT)                                                                                         \
+    do {                                                                                                        \
+        if (cplx_out) {                                                                                         \
+            if (feat_mode == DL4SS_FEAT_NONE) LAUNCH_K1(WT, DL4SS_FEAT_NONE, true);                             \
+            else if (feat_mode == DL4SS_FEAT_ABS) LAUNCH_K1(WT, DL4SS_FEAT_ABS, true);                          \
+            else LAUNCH_K1(WT, DL4SS_FEAT_LOG, true);                                                           \
+        } else {                                                                                                \
+            if (feat_mode == DL4SS_FEAT_ABS) LAUNCH_K1(WT, DL4SS_FEAT_ABS, false);                              \
+            else LAUNCH_K1(WT, DL4SS_FEAT_LOG, false);                                                          \
+        }                                                                                                       \
+    } while (0)
+    if (wav_dtype == DL4SS_WAV_F32) DISPATCH_K1(float);
+    else DISPATCH_K1(double);
+#undef DISPATCH_K1
+#undef LAUNCH_K1
     DL4SS_LAUNCH_CHECK("stft256_kernel");
     return DL4SS_OK;
 }
