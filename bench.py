@@ -43,6 +43,27 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (None when there is none)."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'full_*.md'))):
+        txt = open(path).read()
+        for sec in txt.split('### ')[1:]:
+            if kernel_substr not in sec.split('\n', 1)[0]:
+                continue
+            rd = re.search(r'dram__bytes_read\.sum \| ([0-9.]+) \| (\w+)', sec)
+            wr = re.search(r'dram__bytes_write\.sum \| ([0-9.]+) \| (\w+)', sec)
+            if rd and wr:
+                mul = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+                best = {'bytes_per_launch': float(rd.group(1)) * mul[rd.group(2)] + float(wr.group(1)) * mul[wr.group(2)],
+                        'source': os.path.relpath(path, ROOT)}
+                break
+    return best
+
+
 class ClockSampler(object):
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -491,8 +512,12 @@ def main():
         dom = max(flops, key=lambda k: st[k])
         n_launch = {'rnn_xproj': W['layers'], 'rnn_recurrent': W['layers'], 'emb_attn_mask': 1}[dom]
         ach = flops[dom] / (st[dom] * 1e-3) / 1e12
+        tr = ncu_traffic({'rnn_recurrent': 'rnn_tc_kernel', 'rnn_xproj': 'EpiPlain', 'emb_attn_mask': 'EpiAttn'}[dom])
         roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
-                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
+                'traffic': tr['bytes_per_launch'] if tr else None, 'traffic_source': tr['source'] if tr else None,
+                'algorithmic_bytes_per_launch': (B * (1 + W['L'] // W['hop']) * 2 * (4 if W['cell'] == 'lstm' else 3) * W['H'] * 4
+                                                 + B * (1 + W['L'] // W['hop']) * 2 * W['H'] * 4) if dom == 'rnn_recurrent' else None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
                 'launches_per_step': n_launch, 'ms_per_step': st[dom],
                 'note': 'algorithmic fp32 FLOPs; every tensor-core stage runs bf16x3 (3 MMA products per fp32 product); the recurrent stage is a latency chain of T sequential steps per layer, not throughput bound (DESIGN.md 4)'}

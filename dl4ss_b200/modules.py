@@ -207,8 +207,12 @@ def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=T
     out = torch.empty((B, S, T, F, 2) if complex_mask else (B, S, T, F), device=dev, dtype=torch.float32)
     query = query.contiguous()
     if use_tensor_cores() and E == 50 and S <= 4:
-        rc = lib.dl4ss_emb_attn_mask_tc_fwd(_lib.ptr(split_bf16(h.view(B * T, K)), torch.bfloat16),
-                                            _lib.ptr(weight_planes(weight), torch.bfloat16),
+        # keep both plane tensors referenced until the launch is queued: a temporary freed between two argument
+        # expressions can be handed to the next allocation (e.g. the first-use weight split) and overwritten
+        w_pl = weight_planes(weight)
+        h_pl = split_bf16(h.view(B * T, K))
+        rc = lib.dl4ss_emb_attn_mask_tc_fwd(_lib.ptr(h_pl, torch.bfloat16),
+                                            _lib.ptr(w_pl, torch.bfloat16),
                                             _lib.ptr(bias, name='bias'), _lib.ptr(query, name='query'),
                                             B, T, F, E, K, S, mode, float(config.cRM_k),
                                             float(config.cRM_C if decompress else 0.0), _lib.ptr(out), _lib.stream())
