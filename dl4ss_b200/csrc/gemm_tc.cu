@@ -24,10 +24,12 @@ constexpr int TBM = 128, TBN = 256, TBK = 64, TSTAGES = 2;
 constexpr int TA_BYTES = TBM * TBK * 2;                       // 16 KB
 constexpr int TB_BYTES = TBN * TBK * 2;                       // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
-constexpr int TC_EPI_WARPS = 16;                              // 4 per TMEM sub-partition: each takes a quarter of the columns
-constexpr int TC_EPI_PARTS = TC_EPI_WARPS / 4;
+constexpr int TC_EPI_WARPS = 20;                              // up to 5 per TMEM sub-partition (EpiTraits<>::PARTS of them work)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_STAGE_PITCH = 33;                            // floats per row of a warp's 32x32 store-transpose tile
+constexpr int TC_STORE_WARPS = 8;                             // warps of the plain epilogue (4 sub-partitions x 2 parts)
+constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                           (size_t)TC_STORE_WARPS * 32 * TC_STAGE_PITCH * sizeof(float);
 
 // ------------------------------------------------------------------------------------------ split
 __global__ void __launch_bounds__(256)
@@ -75,15 +77,14 @@ struct EpiAttn {
 };
 
 constexpr int ATT_E = 50;                       // embedding width the fused epilogue is built for
-constexpr int ATT_EP = 64;                      // MMA columns per frequency bin (TMA zero-fills rows 50..63)
-constexpr int ATT_BINS = TBN / ATT_EP;          // 4 frequency bins per N tile
+constexpr int ATT_BINS = TBN / ATT_E;           // 5 frequency bins per N tile, densely packed: columns [50j, 50j+50)
 constexpr int ATT_SMAX = 4;                     // speakers per utterance handled in registers
 
 template <typename Epi> struct EpiTraits;
 // PARTS: epilogue warps per TMEM sub-partition (each takes 1/PARTS of the tile's columns).  The plain store
 // epilogue is bound by its row-strided stores and is fastest with 2, the attention epilogue is math bound: 4.
-template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr bool BINNED = false; static constexpr int PARTS = 2; };
-template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS; static constexpr bool BINNED = true; static constexpr int PARTS = 4; };
+template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr int PARTS = 2; };
+template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS * ATT_E; static constexpr int PARTS = ATT_BINS; };
 
 __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float crm_c) {
     float m = crm_k * tanhf(energy);
@@ -97,81 +98,103 @@ __device__ __forceinline__ float apply_act(float x) {
     return ACT == DL4SS_ACT_TANH ? tanh_f(x) : ACT == DL4SS_ACT_SIGMOID ? sigmoid_f(x) : x;
 }
 
-// chalf: which half of the tile's columns this warp owns
+// Plain store epilogue of one warp: its 32 accumulator rows x (TBN / PARTS) columns, 32 columns at a time.
+// TMEM hands every lane ONE ROW; written out like that a store instruction touches 32 different lines with
+// 16 bytes each.  The 32x32 block is transposed through a per-warp smem tile instead, so that 8 lanes write
+// one row's 128 contiguous bytes (4 full lines per instruction); bias and activation ride the transposed side.
 template <int ACT>
-__device__ __forceinline__ void epilogue_row(const EpiPlain<ACT> &e, uint32_t taddr, int m, int n0, int M, int N, int chalf) {
-    float *crow = e.C + (size_t)m * e.ldc;
+__device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT> &e, uint32_t taddr, int m_base, int n0, int M, int N,
+                                              int part, int lane, float *stage) {
+    constexpr int CH = TBN / 32 / EpiTraits<EpiPlain<ACT>>::PARTS;
     const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
+    const int rsub = lane >> 3, col = (lane & 7) * 4;
 #pragma unroll 1
-    for (int c = chalf * (TBN / 16 / EpiTraits<EpiPlain<ACT>>::PARTS); c < (chalf + 1) * (TBN / 16 / EpiTraits<EpiPlain<ACT>>::PARTS); ++c) {
-        float v[16];
-        tmem_ld16(taddr + c * 16, v);          // warp-collective: executed by every lane
-        if (m >= M) continue;
-        const int n = n0 + c * 16;
-        if (n >= N) continue;
+    for (int cc = part * CH; cc < (part + 1) * CH; ++cc) {
+        float v[32];
+        tmem_ld16(taddr + cc * 32, *reinterpret_cast<float(*)[16]>(&v[0]));       // warp-collective
+        tmem_ld16(taddr + cc * 32 + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+        const int n = n0 + cc * 32;
+        if (n >= N) continue;                                                      // warp-uniform
+        __syncwarp();                                                              // the previous chunk's readers are done
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-            if (vec && n + j + 3 < N) {
-                float4 o;
-                o.x = apply_act<ACT>(v[j] + (e.bias ? __ldg(e.bias + n + j) : 0.f));
-                o.y = apply_act<ACT>(v[j + 1] + (e.bias ? __ldg(e.bias + n + j + 1) : 0.f));
-                o.z = apply_act<ACT>(v[j + 2] + (e.bias ? __ldg(e.bias + n + j + 2) : 0.f));
-                o.w = apply_act<ACT>(v[j + 3] + (e.bias ? __ldg(e.bias + n + j + 3) : 0.f));
-                *reinterpret_cast<float4 *>(crow + n + j) = o;
+        for (int j = 0; j < 32; ++j) stage[lane * TC_STAGE_PITCH + j] = v[j];
+        __syncwarp();
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (e.bias) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (n + col + k < N) bz[k] = __ldg(e.bias + n + col + k);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + rsub;
+            const int m = m_base + row;
+            if (m >= M) continue;
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = apply_act<ACT>(stage[row * TC_STAGE_PITCH + col + k] + bz[k]);
+            float *dst = e.C + (size_t)m * e.ldc + n + col;
+            if (vec && n + col + 3 < N) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
-                for (int jj = j; jj < j + 4; ++jj)
-                    if (n + jj < N) crow[n + jj] = apply_act<ACT>(v[jj] + (e.bias ? __ldg(e.bias + n + jj) : 0.f));
+                for (int k = 0; k < 4; ++k) if (n + col + k < N) dst[k] = o[k];
             }
         }
     }
 }
 
-// n0 = first frequency bin of the tile; bin j of the tile sits in accumulator columns [64j, 64j+50)
-__device__ __forceinline__ void epilogue_row(const EpiAttn &e, uint32_t taddr, int m, int n0, int M, int N, int chalf) {
+// Fused attention epilogue of one warp: frequency bin `part` of the tile (accumulator columns [50*part, 50*part+50)),
+// one accumulator row (b,t) per lane.  n0 = first W row of the tile (a multiple of 50).
+__device__ __forceinline__ void epilogue_tile(const EpiAttn &e, uint32_t taddr, int m_base, int n0, int M, int N,
+                                              int part, int lane, float *stage) {
+    (void)N; (void)stage;
     const int EQ = e.crm ? 2 * ATT_E : ATT_E;
+    const int m = m_base + lane;
     const bool valid = m < M;
     const int mm = valid ? m : 0;
     const int b = mm / e.T, t = mm - b * e.T;
     const float *qb = e.q + (size_t)b * e.S * EQ;
-#pragma unroll 1
-    for (int bin = chalf * (ATT_BINS / EpiTraits<EpiAttn>::PARTS); bin < (chalf + 1) * (ATT_BINS / EpiTraits<EpiAttn>::PARTS); ++bin) {
-        const int f = n0 + bin;
-        const bool fvalid = f < e.F;                      // warp-uniform
-        const float *bias = e.bias + (size_t)(fvalid ? f : 0) * ATT_E;
-        float en[2 * ATT_SMAX];
+    const int f = n0 / ATT_E + part;
+    const bool fvalid = f < e.F;                      // warp-uniform
+    const float *bias = e.bias + (size_t)(fvalid ? f : 0) * ATT_E;
+    float en[2 * ATT_SMAX];
 #pragma unroll
-        for (int s = 0; s < 2 * ATT_SMAX; ++s) en[s] = 0.f;
+    for (int s = 0; s < 2 * ATT_SMAX; ++s) en[s] = 0.f;
 #pragma unroll
-        for (int c = 0; c < ATT_EP / 16; ++c) {
-            float v[16];
-            tmem_ld16(taddr + bin * ATT_EP + c * 16, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int ee = c * 16 + j;                // compile time
-                if (ee >= ATT_E) continue;
-                const float x = tanh_f(v[j] + __ldg(bias + ee));
-#pragma unroll
-                for (int s = 0; s < ATT_SMAX; ++s) {
-                    if (s < e.S) {
-                        en[2 * s] = fmaf(x, __ldg(qb + s * EQ + ee), en[2 * s]);
-                        if (e.crm) en[2 * s + 1] = fmaf(x, __ldg(qb + s * EQ + ATT_E + ee), en[2 * s + 1]);
-                    }
-                }
-            }
+    for (int c = 0; c < 4; ++c) {                     // 16 + 16 + 16 + 2 columns
+        float v[16];
+        if (c < 3) {
+            tmem_ld16(taddr + part * ATT_E + c * 16, v);
+        } else {
+            float v2[2];
+            tmem_ld2(taddr + part * ATT_E + 48, v2);
+            v[0] = v2[0]; v[1] = v2[1];
         }
-        if (valid && fvalid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int ee = c * 16 + j;                // compile time
+            if (ee >= ATT_E) continue;
+            const float x = tanh_f(v[j] + __ldg(bias + ee));
 #pragma unroll
             for (int s = 0; s < ATT_SMAX; ++s) {
                 if (s < e.S) {
-                    const size_t o = (((size_t)b * e.S + s) * e.T + t) * e.F + f;
-                    if (!e.crm) {
-                        e.out[o] = sigmoid_f(en[2 * s]);
-                    } else {
-                        reinterpret_cast<float2 *>(e.out)[o] =
-                            make_float2(crm_value_tc(en[2 * s], e.crm_k, e.crm_c),
-                                        crm_value_tc(en[2 * s + 1], e.crm_k, e.crm_c));
-                    }
+                    en[2 * s] = fmaf(x, __ldg(qb + s * EQ + ee), en[2 * s]);
+                    if (e.crm) en[2 * s + 1] = fmaf(x, __ldg(qb + s * EQ + ATT_E + ee), en[2 * s + 1]);
+                }
+            }
+        }
+    }
+    if (valid && fvalid) {
+#pragma unroll
+        for (int s = 0; s < ATT_SMAX; ++s) {
+            if (s < e.S) {
+                const size_t o = (((size_t)b * e.S + s) * e.T + t) * e.F + f;
+                if (!e.crm) {
+                    e.out[o] = sigmoid_f(en[2 * s]);
+                } else {
+                    reinterpret_cast<float2 *>(e.out)[o] =
+                        make_float2(crm_value_tc(en[2 * s], e.crm_k, e.crm_c),
+                                    crm_value_tc(en[2 * s + 1], e.crm_k, e.crm_c));
                 }
             }
         }
@@ -220,13 +243,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     mbar_expect_tx(&full[stage], TSTAGE_BYTES);
                     tma_load_3d(st, &tmap_a, &full[stage], kb * TBK, m0, 0);
                     tma_load_3d(st + TA_BYTES, &tmap_a, &full[stage], kb * TBK, m0, 1);
-                    if (EpiTraits<Epi>::BINNED) {      // W viewed [plane][F][E][K]: 4 bins x 64 (50 real) rows
-                        tma_load_4d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, 0, n0, 0);
-                        tma_load_4d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, 0, n0, 1);
-                    } else {
-                        tma_load_3d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
-                        tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
-                    }
+                    tma_load_3d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
+                    tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
                     if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -261,14 +279,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
     } else if (((warp - 2) >> 2) < EpiTraits<Epi>::PARTS) {
         const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter ..
-        const int chalf = (warp - 2) >> 2;            // column part of the tile
+        const int part = (warp - 2) >> 2;             // column part of the tile
+        float *stage = reinterpret_cast<float *>(tiles + (size_t)TSTAGES * TSTAGE_BYTES + 256) +
+                       (size_t)((part * 4 + quarter) % TC_STORE_WARPS) * 32 * TC_STAGE_PITCH;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TBN;
-            epilogue_row(epi, taddr, m0 + quarter * 32 + lane, n0, M, N, chalf);
+            epilogue_tile(epi, taddr, m0 + quarter * 32, n0, M, N, part, lane, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -318,22 +338,14 @@ static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int
     return make_bf16_map(map, planes, 3, dims, strides, box);
 }
 
-// W planes bf16 [2][F*E][Kp] viewed as [2][F][E][Kp]; box = 64 (K) x 64 (E, rows >= E zero-filled) x 4 bins
-static int make_binned_map(CUtensorMap *map, const void *planes, int F, int E, int Kp) {
-    cuuint64_t dims[4] = {(cuuint64_t)Kp, (cuuint64_t)E, (cuuint64_t)F, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)Kp * 2, (cuuint64_t)E * Kp * 2, (cuuint64_t)F * E * Kp * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)ATT_EP, (cuuint32_t)ATT_BINS, 1};
-    return make_bf16_map(map, planes, 4, dims, strides, box);
-}
-
 template <typename Epi>
 static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, int K, int n_tiles, const Epi &epi,
-                     cudaStream_t st, int binned_F = 0) {
+                     cudaStream_t st) {
     const int Kp = (K + TBK - 1) / TBK * TBK;
     CUtensorMap ma, mb;
     int rc = make_plane_map(&ma, a_planes, M, Kp, TBM);
     if (rc) return rc;
-    rc = binned_F ? make_binned_map(&mb, w_planes, binned_F, ATT_E, Kp) : make_plane_map(&mb, w_planes, N, Kp, TBN);
+    rc = make_plane_map(&mb, w_planes, N, Kp, TBN);        // rows past N (and past a tile's own rows) are ignored / zero
     if (rc) return rc;
     const int m_tiles = cdiv(M, TBM);
     const long long total = (long long)m_tiles * n_tiles;
@@ -397,5 +409,5 @@ extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_pl
     if (B == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG((long long)B * T < (1ll << 31), "emb_attn_mask_tc_fwd: B*T too large");
     EpiAttn e{bias, q, mask_out, T, F, S, mode == DL4SS_ATT_DOT_CRM ? 1 : 0, crm_k, crm_c};
-    return launch_tc(h_planes, w_planes, B * T, F * E, K, cdiv(F, ATT_BINS), e, (cudaStream_t)stream, F);
+    return launch_tc(h_planes, w_planes, B * T, F * E, K, cdiv(F, ATT_BINS), e, (cudaStream_t)stream);
 }
