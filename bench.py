@@ -309,7 +309,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'separated_audio_seconds_per_second', 'value': v, 'unit': 'audio-s/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n_utt),
+            'config': workload_config(args.batch),
             'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d utterances x 5 s per step (bounded sample of the batch-256 workload)' % n_utt},
             'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -410,7 +410,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='utterances per GPU per step')
-    ap.add_argument('--ref-utts', type=int, default=8, help='utterances per step of the CPU reference arm')
+    ap.add_argument('--ref-utts', type=int, default=16, help='utterances per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-utts', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
