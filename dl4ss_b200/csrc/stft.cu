@@ -167,6 +167,90 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
     }
 }
 
+// Masked spectra of two (source, frame) items -> one complex inverse transform: on return v[n1].x / .y hold the
+// (unnormalised, unwindowed) time samples 16*n1 + l16 of item a / item b.
+template <int MASK_KIND>
+__device__ __forceinline__ void masked_pair_ifft(const float *__restrict__ mask, const float2 *__restrict__ spec,
+                                                 int b, int S, int T, int sa, int ta, bool va, int sb, int tb, bool vb,
+                                                 int l16, float2 *xch_g, const float2 *tw, float2 (&v)[16]) {
+    const int src = (16 - l16) & 15;
+    float2 pa[8], pb[8], pa_n = make_float2(0.f, 0.f), pb_n = make_float2(0.f, 0.f);
+    if (MASK_KIND == DL4SS_MASK_NONE) {
+        const float2 *ra = spec + (((size_t)b * S + sa) * T + ta) * NBIN;
+        const float2 *rb = spec + (((size_t)b * S + sb) * T + tb) * NBIN;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            pa[m] = va ? ra[16 * m + l16] : make_float2(0.f, 0.f);
+            pb[m] = vb ? rb[16 * m + l16] : make_float2(0.f, 0.f);
+        }
+        if (l16 == 0) {
+            if (va) pa_n = ra[128];
+            if (vb) pb_n = rb[128];
+        }
+    } else {
+        const float2 *xa = spec + ((size_t)b * T + ta) * NBIN;
+        const float2 *xb = spec + ((size_t)b * T + tb) * NBIN;
+        const size_t ma = (((size_t)b * S + sa) * T + ta) * NBIN;
+        const size_t mb = (((size_t)b * S + sb) * T + tb) * NBIN;
+        float2 xva[8], xvb[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            xva[m] = va ? xa[16 * m + l16] : make_float2(0.f, 0.f);
+            xvb[m] = vb ? xb[16 * m + l16] : make_float2(0.f, 0.f);
+        }
+        if (MASK_KIND == DL4SS_MASK_REAL) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float ka = va ? mask[ma + 16 * m + l16] : 0.f;
+                float kb = vb ? mask[mb + 16 * m + l16] : 0.f;
+                pa[m] = make_float2(ka * xva[m].x, ka * xva[m].y);
+                pb[m] = make_float2(kb * xvb[m].x, kb * xvb[m].y);
+            }
+            if (l16 == 0) {
+                if (va) { float k = mask[ma + 128]; float2 x = xa[128]; pa_n = make_float2(k * x.x, k * x.y); }
+                if (vb) { float k = mask[mb + 128]; float2 x = xb[128]; pb_n = make_float2(k * x.x, k * x.y); }
+            }
+        } else {
+            const float2 *cma = reinterpret_cast<const float2 *>(mask) + ma;
+            const float2 *cmb = reinterpret_cast<const float2 *>(mask) + mb;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float2 ka = va ? cma[16 * m + l16] : make_float2(0.f, 0.f);
+                float2 kb = vb ? cmb[16 * m + l16] : make_float2(0.f, 0.f);
+                // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
+                pa[m] = make_float2(ka.x * xva[m].x - ka.y * xva[m].y, ka.x * xva[m].y + ka.y * xva[m].x);
+                pb[m] = make_float2(kb.x * xvb[m].x - kb.y * xvb[m].y, kb.x * xvb[m].y + kb.y * xvb[m].x);
+            }
+            if (l16 == 0) {
+                if (va) { float2 k = cma[128]; float2 x = xa[128]; pa_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+                if (vb) { float2 k = cmb[128]; float2 x = xb[128]; pb_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+            }
+        }
+    }
+    if (l16 == 0) {   // DC bin: irfft ignores the imaginary part
+        pa[0].y = 0.f;
+        pb[0].y = 0.f;
+    }
+    // Z[k] = A[k] + i*B[k] for k <= 128 ; Z[256-k] = conj(A[k]) + i*conj(B[k])
+    float2 c[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        v[m] = make_float2(pa[m].x - pb[m].y, pa[m].y + pb[m].x);
+        c[m] = make_float2(pa[m].x + pb[m].y, pb[m].x - pa[m].y);
+    }
+#pragma unroll
+    for (int m = 8; m < 16; ++m) {
+        float cx = __shfl_sync(0xffffffffu, c[15 - m].x, src, 16);
+        float cy = __shfl_sync(0xffffffffu, c[15 - m].y, src, 16);
+        if (l16 == 0) {
+            if (m == 8) { cx = pa_n.x; cy = pb_n.x; }
+            else { cx = c[16 - m].x; cy = c[16 - m].y; }
+        }
+        v[m] = make_float2(cx, cy);
+    }
+    fft256_group<true>(v, l16, xch_g, tw);
+}
+
 // ------------------------------------------------------------------------------------ K6
 // One CTA reconstructs `bpt` hop-blocks of every source of one utterance.  It transforms the
 // frames that touch those blocks (a leading halo of ceil(256/hop)-1 frames is recomputed by the
@@ -209,7 +293,6 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     __syncthreads();
 
     const int g = tid >> 4, l16 = tid & 15;
-    const int src = (16 - l16) & 15;
     const int rounds = (npairs + STFT_GROUPS - 1) / STFT_GROUPS;
     for (int r = 0; r < rounds; ++r) {
         const int p = r * STFT_GROUPS + g;
@@ -218,81 +301,8 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
         const int ta = t_lo + (va ? ia / S : 0), sa = va ? ia % S : 0;
         const int tb = t_lo + (vb ? ib / S : 0), sb = vb ? ib % S : 0;
 
-        float2 pa[8], pb[8], pa_n = make_float2(0.f, 0.f), pb_n = make_float2(0.f, 0.f);
-        if (MASK_KIND == DL4SS_MASK_NONE) {
-            const float2 *ra = spec + (((size_t)b * S + sa) * T + ta) * NBIN;
-            const float2 *rb = spec + (((size_t)b * S + sb) * T + tb) * NBIN;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                pa[m] = va ? ra[16 * m + l16] : make_float2(0.f, 0.f);
-                pb[m] = vb ? rb[16 * m + l16] : make_float2(0.f, 0.f);
-            }
-            if (l16 == 0) {
-                if (va) pa_n = ra[128];
-                if (vb) pb_n = rb[128];
-            }
-        } else {
-            const float2 *xa = spec + ((size_t)b * T + ta) * NBIN;
-            const float2 *xb = spec + ((size_t)b * T + tb) * NBIN;
-            const size_t ma = (((size_t)b * S + sa) * T + ta) * NBIN;
-            const size_t mb = (((size_t)b * S + sb) * T + tb) * NBIN;
-            float2 xva[8], xvb[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                xva[m] = va ? xa[16 * m + l16] : make_float2(0.f, 0.f);
-                xvb[m] = vb ? xb[16 * m + l16] : make_float2(0.f, 0.f);
-            }
-            if (MASK_KIND == DL4SS_MASK_REAL) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    float ka = va ? mask[ma + 16 * m + l16] : 0.f;
-                    float kb = vb ? mask[mb + 16 * m + l16] : 0.f;
-                    pa[m] = make_float2(ka * xva[m].x, ka * xva[m].y);
-                    pb[m] = make_float2(kb * xvb[m].x, kb * xvb[m].y);
-                }
-                if (l16 == 0) {
-                    if (va) { float k = mask[ma + 128]; float2 x = xa[128]; pa_n = make_float2(k * x.x, k * x.y); }
-                    if (vb) { float k = mask[mb + 128]; float2 x = xb[128]; pb_n = make_float2(k * x.x, k * x.y); }
-                }
-            } else {
-                const float2 *cma = reinterpret_cast<const float2 *>(mask) + ma;
-                const float2 *cmb = reinterpret_cast<const float2 *>(mask) + mb;
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    float2 ka = va ? cma[16 * m + l16] : make_float2(0.f, 0.f);
-                    float2 kb = vb ? cmb[16 * m + l16] : make_float2(0.f, 0.f);
-                    // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
-                    pa[m] = make_float2(ka.x * xva[m].x - ka.y * xva[m].y, ka.x * xva[m].y + ka.y * xva[m].x);
-                    pb[m] = make_float2(kb.x * xvb[m].x - kb.y * xvb[m].y, kb.x * xvb[m].y + kb.y * xvb[m].x);
-                }
-                if (l16 == 0) {
-                    if (va) { float2 k = cma[128]; float2 x = xa[128]; pa_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
-                    if (vb) { float2 k = cmb[128]; float2 x = xb[128]; pb_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
-                }
-            }
-        }
-        if (l16 == 0) {   // DC bin: irfft ignores the imaginary part
-            pa[0].y = 0.f;
-            pb[0].y = 0.f;
-        }
-        // Z[k] = A[k] + i*B[k] for k <= 128 ; Z[256-k] = conj(A[k]) + i*conj(B[k])
-        float2 v[16], c[8];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            v[m] = make_float2(pa[m].x - pb[m].y, pa[m].y + pb[m].x);
-            c[m] = make_float2(pa[m].x + pb[m].y, pb[m].x - pa[m].y);
-        }
-#pragma unroll
-        for (int m = 8; m < 16; ++m) {
-            float cx = __shfl_sync(0xffffffffu, c[15 - m].x, src, 16);
-            float cy = __shfl_sync(0xffffffffu, c[15 - m].y, src, 16);
-            if (l16 == 0) {
-                if (m == 8) { cx = pa_n.x; cy = pb_n.x; }
-                else { cx = c[16 - m].x; cy = c[16 - m].y; }
-            }
-            v[m] = make_float2(cx, cy);
-        }
-        fft256_group<true>(v, l16, xch + g * DL4SS_XCH_FLOAT2, tw);
+        float2 v[16];
+        masked_pair_ifft<MASK_KIND>(mask, spec, b, S, T, sa, ta, va, sb, tb, vb, l16, xch + g * DL4SS_XCH_FLOAT2, tw, v);
         float *ya = ybuf + (size_t)ia * NFFT;
         float *yb = ybuf + (size_t)ib * NFFT;
 #pragma unroll
@@ -392,6 +402,85 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
     }
 }
 
+// ------------------------------------------------------------------------------------ K6, hop = n_fft/2
+// Every reference config has hop 128 = half a frame: exactly two frames cover each output sample.  A 16-lane
+// group transforms the frame pair (2q, 2q+1) of ONE source, so the hop block between them is summed, normalised
+// and stored straight from registers; the block after frame 2q+1 needs the lower half of the NEXT pair's first
+// frame, which every group parks in an 8 KB exchange buffer (one __syncthreads).  No frame buffer, no separate
+// overlap-add pass; the group after the tile's last pair is recomputed as halo by the neighbouring CTA.
+constexpr int K6H_PAIRS = STFT_GROUPS - 1;       // pairs a CTA owns (the 16th group is the halo pair)
+
+template <int MASK_KIND>
+__global__ void __launch_bounds__(STFT_THREADS)
+istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec, int S, int T, int tiles_per_src,
+                  const float *__restrict__ window, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *xch = tw + 256;
+    float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);   // 256: window / N
+    float *inv = win + NFFT;                                                        // 128: 1 / (w^2[j] + w^2[j+128])
+    float *exch = inv + NFFT / 2;                                                   // [groups][128]
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int s = bid % S; bid /= S;                 // sources of an utterance run back to back: X stays in L2
+    const int tile = bid % tiles_per_src;
+    const int b = bid / tiles_per_src;
+    const int Lout = (NFFT / 2) * (T - 1);
+
+    tw[tid] = g_tw256[tid];
+    {
+        const float wt = window[tid];
+        win[tid] = wt * (1.0f / NFFT);
+        if (tid < NFFT / 2) {
+            const float w2 = window[tid + NFFT / 2];
+            const float e = wt * wt + w2 * w2;
+            inv[tid] = (e > 1.17549435e-38f) ? 1.0f / e : 1.0f;
+        }
+    }
+    __syncthreads();
+
+    const int g = tid >> 4, l16 = tid & 15;
+    const int q = tile * K6H_PAIRS + g;              // group K6H_PAIRS is the halo pair
+    const int ta = 2 * q, tb = 2 * q + 1;
+    const bool va = ta < T, vb = (tb < T) && (g < K6H_PAIRS);     // the halo group only needs its first frame
+
+    float2 v[16];
+    masked_pair_ifft<MASK_KIND>(mask, spec, b, S, T, s, va ? ta : 0, va, s, vb ? tb : 0, vb, l16,
+                                xch + g * DL4SS_XCH_FLOAT2, tw, v);
+
+    // park the windowed lower half of the first frame for the previous group
+    float *ex = exch + g * (NFFT / 2);
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+        const int j = 16 * n1 + l16;
+        ex[j] = v[n1].x * win[j];
+    }
+    __syncthreads();
+    if (g >= K6H_PAIRS) return;
+
+    float *o = out + ((size_t)b * S + s) * Lout;
+    // block 2q: frame 2q upper half + frame 2q+1 lower half (both in registers)
+    if (tb <= T - 1) {
+        float *ob = o + (size_t)ta * (NFFT / 2) + l16;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int j = 16 * n1 + l16;
+            ob[16 * n1] = (v[n1 + 8].x * win[j + NFFT / 2] + v[n1].y * win[j]) * inv[j];
+        }
+    }
+    // block 2q+1: frame 2q+1 upper half + the next pair's first frame lower half
+    if (tb + 1 <= T - 1) {
+        const float *nx = exch + (g + 1) * (NFFT / 2);
+        float *ob = o + (size_t)tb * (NFFT / 2) + l16;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int j = 16 * n1 + l16;
+            ob[16 * n1] = (v[n1 + 8].y * win[j + NFFT / 2] + nx[j]) * inv[j];
+        }
+    }
+}
+
 }  // namespace dl4ss
 
 using namespace dl4ss;
@@ -457,6 +546,28 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
         return DL4SS_EUNSUPPORTED;
     }
     if (B == 0 || T == 1) return DL4SS_OK;     // hop*(T-1) == 0 samples
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if (hop == NFFT / 2) {          // the reference's hop: fused pair kernel
+        { int rc = ensure_twiddles(st0); if (rc) return rc; }
+        const int pairs = (T + 1) / 2;
+        const int tiles_h = cdiv(pairs, K6H_PAIRS);
+        const size_t smem_h = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
+                              (NFFT + NFFT / 2) * sizeof(float) + (size_t)STFT_GROUPS * (NFFT / 2) * sizeof(float);
+        const long long grid_h = (long long)B * S * tiles_h;
+        DL4SS_CHECK_ARG(grid_h < (1ll << 31), "mask_istft: grid too large");
+#define LAUNCH_H128(KIND)                                                                                       \
+        do {                                                                                                    \
+            DL4SS_CUDA(cudaFuncSetAttribute(istft_h128_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h)); \
+            istft_h128_kernel<KIND><<<(unsigned)grid_h, STFT_THREADS, smem_h, st0>>>(                           \
+                mask, (const float2 *)spec, S, T, tiles_h, window, wav_out);                                    \
+        } while (0)
+        if (mask_kind == DL4SS_MASK_NONE) LAUNCH_H128(DL4SS_MASK_NONE);
+        else if (mask_kind == DL4SS_MASK_REAL) LAUNCH_H128(DL4SS_MASK_REAL);
+        else LAUNCH_H128(DL4SS_MASK_COMPLEX);
+#undef LAUNCH_H128
+        DL4SS_LAUNCH_CHECK("istft_h128_kernel");
+        return DL4SS_OK;
+    }
     const int halo = (NFFT - 1) / hop;         // frames before the first block's own frame
     const int nblocks = T - 1;
     // frames per CTA: aim at 32 (frame,source) items = one round of 16 two-frame groups
