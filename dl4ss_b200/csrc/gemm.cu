@@ -148,6 +148,7 @@ int linear_fwd_impl(const float *A, int lda, const float *W, int ldw, const floa
 
 extern "C" int dl4ss_linear_fwd(const float *A, int lda, const float *W, int ldw, const float *bias,
                                 float *C, int ldc, int M, int N, int K, int act, void *stream) {
+    if (M == 0) return DL4SS_OK;                 // empty batch (pointers may be null)
     DL4SS_CHECK_ARG(A && W && C, "linear_fwd: null operand");
     DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "linear_fwd: bad M/N/K %d/%d/%d", M, N, K);
     DL4SS_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "linear_fwd: pitch smaller than row");

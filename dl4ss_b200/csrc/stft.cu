@@ -488,6 +488,7 @@ using namespace dl4ss;
 extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int n_fft, int hop,
                                const float *window, int feat_mode, float eps, int conj,
                                float *feat_out, float *cplx_out, void *stream) {
+    if (B == 0) return DL4SS_OK;                 // empty batch: nothing to read or write (pointers may be null)
     DL4SS_CHECK_ARG(wav && window, "stft_feat: null wav/window");
     DL4SS_CHECK_ARG(B >= 0 && L > n_fft / 2, "stft_feat: need B>=0 and L > n_fft/2 (reflect pad), got B=%d L=%d", B, L);
     DL4SS_CHECK_ARG(hop >= 1 && hop <= n_fft, "stft_feat: hop must be in [1,n_fft], got %d", hop);
@@ -536,6 +537,7 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
 extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *spec, int B, int S,
                                 int T, int n_fft, int hop, const float *window, float *wav_out,
                                 void *stream) {
+    if (B == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG(spec && window && wav_out, "mask_istft: null spec/window/out");
     DL4SS_CHECK_ARG(mask_kind >= DL4SS_MASK_NONE && mask_kind <= DL4SS_MASK_COMPLEX, "mask_istft: bad mask_kind %d", mask_kind);
     DL4SS_CHECK_ARG(mask_kind == DL4SS_MASK_NONE || mask, "mask_istft: mask is null");

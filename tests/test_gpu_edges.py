@@ -1,0 +1,108 @@
+"""Edge cases of the CUDA path (ragged / empty / maximum shapes), each against torch on the CPU oracle side."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rnn_pair(cell, layers, H, T, seed=1):
+    import dl4ss_b200 as d
+    torch.manual_seed(seed)
+    rnn = {'lstm': torch.nn.LSTM, 'gru': torch.nn.GRU}[cell](129, H, layers, batch_first=True, bidirectional=True)
+    d.config.HIDDEN_UNITS, d.config.NUM_LAYERS = H, layers
+    ours = d.MIX_SPEECH(129, T, cell=cell, num_layers=layers).cuda()
+    ours.layer.load_state_dict(rnn.state_dict())
+    return rnn, ours
+
+
+@pytest.mark.parametrize('cell,H,B,T', [('lstm', 100, 5, 9), ('gru', 200, 33, 7), ('lstm', 320, 4, 6), ('lstm', 300, 257, 4),
+                                         ('gru', 300, 65, 3), ('lstm', 300, 1, 1), ('lstm', 60, 3, 5), ('gru', 90, 2, 5)])
+def test_recurrent_shapes(cuda, cell, H, B, T):
+    """Every supported hidden size of the tcgen05 kernel (multiples of 20 up to 320), batch sizes that leave
+    partial tiles, need a second tile per CTA, or a second launch (> 256), T = 1, and a size that falls back to the
+    fp32 CUDA-core kernel (H = 90: a multiple of 10, not of 20)."""
+    import dl4ss_b200 as d
+    try:
+        rnn, ours = _rnn_pair(cell, 1, H, T)
+        x = torch.rand(B, T, 129)
+        with torch.no_grad():
+            y_ref, _ = rnn(x)
+            y = ours.encode(x.cuda()).cpu()
+        assert (y - y_ref).abs().max().item() < 2e-5
+    finally:
+        d.config.HIDDEN_UNITS, d.config.NUM_LAYERS = 300, 2
+
+
+def test_empty_batches(cuda):
+    import dl4ss_b200 as d
+    f, c = d.stft_features(torch.zeros(0, 4000, device=cuda), 256, 128)
+    assert tuple(f.shape) == (0, 32, 129) and tuple(c.shape) == (0, 32, 129, 2)
+    w = d.mask_istft(torch.zeros(0, 2, 32, 129, device=cuda), c, 128)
+    assert tuple(w.shape) == (0, 2, 128 * 31)
+    assert tuple(d.linear_fwd(torch.zeros(0, 7, device=cuda), torch.zeros(5, 7, device=cuda)).shape) == (0, 5)
+
+
+@pytest.mark.parametrize('S,cplx', [(1, False), (4, False), (4, True), (1, True)])
+def test_speaker_counts(cuda, S, cplx):
+    """S = 1 and the largest S the fused epilogue keeps in registers (4; cRM: 8 energies)."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    B, T = 2, 9
+    ref, ours = build_pair('gru' if cplx else 'lstm', 1, 129, T, cplx)
+    if cplx:
+        with torch.no_grad():
+            ref['emb'].layer.weight.mul_(0.1)
+            ours['emb'].layer.weight.mul_(0.1)
+    torch.manual_seed(2)
+    feas = torch.rand(B, T, 129)
+    mag = torch.randn(B, T, 129, 2)
+    idx = np.sort(np.random.RandomState(S).choice(101, (B, S)), axis=1)
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, idx, mag)
+    m = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj']).masks(feas.cuda(), idx).cpu()
+    scale = torch.clamp(r['masks'].abs(), min=10.0) if cplx else 1.0
+    assert ((m - r['masks']).abs() / scale).max().item() < 1e-4
+    d.config.is_ComlexMask = False
+
+
+@pytest.mark.parametrize('hop,L', [(256, 4096), (64, 1000), (128, 129), (128, 40001)])
+def test_stft_istft_edge_lengths(cuda, hop, L):
+    """hop = n_fft (no overlap), the shortest signal reflect padding allows, and L not a multiple of hop."""
+    import dl4ss_b200 as d
+    from oracle import stft_ref as sr
+    rng = np.random.RandomState(L)
+    wav = rng.standard_normal((2, L))
+    ref = np.stack([sr.stft_ref(w, 256, hop).T for w in wav])
+    _, c = d.stft_features(torch.from_numpy(wav).cuda(), 256, hop, 'hann', None)
+    got = torch.view_as_complex(c).cpu().numpy()
+    assert np.abs(got - ref).max() < 1e-4 * np.abs(ref).max()
+    T = ref.shape[1]
+    if T > 1:
+        back_ref = np.stack([sr.istft_ref(r.T, hop) for r in ref])
+        back = d.mask_istft(None, c.view(2, 1, T, 129, 2), hop).cpu().numpy()[:, 0]
+        # where the window sum-square is tiny (hop = n_fft: frame edges of the Hann window) librosa's division
+        # amplifies fp32 round-off by 1/w; compare where the envelope is well conditioned
+        wss = sr.window_sumsquare('hann', T, 256, hop)[128:128 + back.shape[1]]
+        ok = wss > 1e-2
+        assert np.abs(back - back_ref)[:, ok].max() < 1e-4 * np.abs(back_ref).max()
+
+
+def test_errors_are_loud(cuda):
+    import dl4ss_b200 as d
+    rnn, ours = _rnn_pair('lstm', 1, 304, 4)              # neither kernel has a 304-unit decomposition
+    try:
+        with pytest.raises(RuntimeError, match='multiple'):
+            ours.encode(torch.zeros(2, 4, 129, device=cuda))
+    finally:
+        d.config.HIDDEN_UNITS, d.config.NUM_LAYERS = 300, 2
+    with pytest.raises(RuntimeError):
+        d.stft_features(torch.zeros(1, 100, device=cuda), 256, 128)          # L <= n_fft/2
+    with pytest.raises(RuntimeError):
+        d.stft_features(torch.zeros(1, 4000, device=cuda), 512, 128)         # only the 256-point transform
+    with pytest.raises(RuntimeError):
+        d.mask_istft(torch.zeros(1, 2, 5, 129, device=cuda), torch.zeros(1, 6, 129, 2, device=cuda), 128)
+    with pytest.raises(RuntimeError):
+        d.linear_fwd(torch.zeros(2, 3, device=cuda).t(), torch.zeros(4, 2, device=cuda))   # non-contiguous
