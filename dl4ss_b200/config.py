@@ -46,3 +46,7 @@ GEMM_PRECISION = 'bf16x3'
 # Not in the reference: run the recurrent product h*W_hh^T on tcgen05 (persistent tensor-core kernel)
 # when GEMM_PRECISION == 'bf16x3' and H is supported; False selects the fp32 CUDA-core recurrent kernel.
 RNN_TENSOR_CORES = True
+
+# Not in the reference: the training step keeps static per-layer buffers and replays the T-step BPTT chain
+# (launch bound: one library GEMM + one gate kernel per time step) from a CUDA graph captured on first use.
+TRAIN_CUDA_GRAPHS = True

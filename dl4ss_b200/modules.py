@@ -147,10 +147,11 @@ def whh_planes(lw, cell, H):
     return pl
 
 
-def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None):
+def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None, y=None):
     """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]."""
     lib = _lib.load()
-    y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
+    if y is None:
+        y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
     if tc_rec:
         rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(whh_planes(lw, cell, H), torch.bfloat16),
                                         _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
@@ -164,9 +165,10 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     return y
 
 
-def rnn_forward(packed, x, save=None):
+def rnn_forward(packed, x, save=None, buffers=None):
     """Bidirectional multi-layer LSTM/GRU forward, batch_first, zero initial state.
-    x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward."""
+    x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward; `buffers` (list of dicts
+    with 'y', 'gates', 'cells' per layer) makes the layers write into caller-owned static tensors."""
     lib = _lib.load()
     rnn = packed.rnn
     gru = isinstance(rnn, nn.GRU)
@@ -179,17 +181,19 @@ def rnn_forward(packed, x, save=None):
     ws = recurrent_workspace(B, T, H, cell, tc_rec, dev)
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
-    for lw in packed.get():
+    for li, lw in enumerate(packed.get()):
         if use_tensor_cores():
             x2d = inp.view(B * T, -1)
             linear_tc(split_bf16(x2d), weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
         else:
             linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
-        gates = cells = None
-        if save is not None:
+        gates = cells = y_out = None
+        if buffers is not None:
+            gates, cells, y_out = buffers[li]['gates'], buffers[li]['cells'], buffers[li]['y']
+        elif save is not None:
             gates = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
             cells = torch.empty(B, T, 2, H, device=dev, dtype=torch.float32)
-        y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells)
+        y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells, y_out)
         if save is not None:
             save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
         inp = y

@@ -88,6 +88,7 @@ class TrainStep(object):
         self.mix, self.emb, self.att = mix_hidden_layer_3d, mix_speech_multiEmbedding, att_speech_layer
         self.adj = adjust_layer if (adjust_layer is not None and config.is_SelfTune) else None
         self.complex_mask = bool(config.is_ComlexMask)
+        self._bptt = {}           # (layer, B, T) -> static buffers + captured BPTT graph
 
     def parameters(self):
         mods = [self.mix, self.emb] + ([self.adj] if self.adj is not None else [])
@@ -104,7 +105,10 @@ class TrainStep(object):
         lin = self.mix.Linear
         E = lin.out_features // F
         saved = []
-        hidden = M.rnn_forward(self.mix._packed, mix_feas, save=saved)            # K2 + K3, gates saved
+        bufs = None
+        if config.TRAIN_CUDA_GRAPHS:       # static per-layer buffers so the BPTT chain can be replayed from a graph
+            bufs = [self._bptt_state(l, B, T, mix_feas.device) for l in range(self.mix.layer.num_layers)]
+        hidden = M.rnn_forward(self.mix._packed, mix_feas, save=saved, buffers=bufs)   # K2 + K3, gates saved
         idx = self.emb.index_tensor(spk_idx)
         table = self.emb.layer.weight
         e = table.detach()[idx]                                                   # [B,S,EQ] gather (glue)
@@ -203,8 +207,34 @@ class TrainStep(object):
         # encoder backward, top layer first
         self.rnn_backward(ctx, dh.contiguous())
 
-    def rnn_backward(self, ctx, dy):
+    def _bptt_state(self, l, B, T, dev):
+        key = (l, B, T)
+        st = self._bptt.get(key)
+        if st is None:
+            rnn = self.mix.layer
+            G = 3 if isinstance(rnn, nn.GRU) else 4
+            H = rnn.hidden_size
+            f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+            st = {'y': f(B, T, 2 * H), 'gates': f(B, T, 2, G * H), 'cells': f(B, T, 2, H), 'dy': f(B, T, 2 * H),
+                  'dgx': f(B, T, 2, G * H), 'dgh': f(B, T, 2, G * H) if G == 3 else None, 'carry': f(2, B, H),
+                  'dg_cur': f(2, B, G * H), 'dh_rec': f(2, B, H), 'whh': f(2, G * H, H), 'graph': None}
+            self._bptt[key] = st
+        return st
+
+    def _bptt_chain(self, cell, st, B, T, H):
+        """The T-step BPTT chain of one layer: per step one library GEMM (dh_rec = dgates x W_hh, both directions
+        batched) and one gate kernel."""
         lib = _lib.load()
+        for s in range(T):
+            if s > 0:
+                torch.bmm(st['dg_cur'], st['whh'], out=st['dh_rec'])
+            rc = lib.dl4ss_rnn_bwd_step(cell, s, _lib.ptr(st['dy']), _lib.ptr(st['dh_rec']), _lib.ptr(st['gates']),
+                                        _lib.ptr(st['cells']), _lib.ptr(st['y']), _lib.ptr(st['carry']),
+                                        _lib.ptr(st['dgx']), _lib.ptr(st['dgh']), _lib.ptr(st['dg_cur']), B, T, H,
+                                        _lib.stream())
+            _lib.check(rc, 'dl4ss_rnn_bwd_step')
+
+    def rnn_backward(self, ctx, dy):
         rnn = self.mix.layer
         gru = isinstance(rnn, nn.GRU)
         cell = _lib.CELL_GRU if gru else _lib.CELL_LSTM
@@ -213,21 +243,35 @@ class TrainStep(object):
         B, T = ctx['B'], ctx['T']
         dev = dy.device
         layers = self.mix._packed.get()
+        use_graph = bool(config.TRAIN_CUDA_GRAPHS)
         for l in range(rnn.num_layers - 1, -1, -1):
             sv, lw = ctx['saved'][l], layers[l]
-            whh = lw['whh']                                                      # [2,G*H,H]
-            dgx = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
-            dgh = torch.empty_like(dgx) if gru else None
-            carry = torch.empty(2, B, H, device=dev, dtype=torch.float32)
-            dg_cur = torch.empty(2, B, G * H, device=dev, dtype=torch.float32)
-            dh_rec = torch.empty(2, B, H, device=dev, dtype=torch.float32)
-            for s in range(T):
-                if s > 0:
-                    torch.bmm(dg_cur, whh, out=dh_rec)                           # per-step recurrent GEMM (cuBLAS)
-                rc = lib.dl4ss_rnn_bwd_step(cell, s, _lib.ptr(dy), _lib.ptr(dh_rec), _lib.ptr(sv['gates']),
-                                            _lib.ptr(sv['cells']), _lib.ptr(sv['y']), _lib.ptr(carry), _lib.ptr(dgx),
-                                            _lib.ptr(dgh), _lib.ptr(dg_cur), B, T, H, _lib.stream())
-                _lib.check(rc, 'dl4ss_rnn_bwd_step')
+            if use_graph:
+                st = self._bptt_state(l, B, T, dev)          # y / gates / cells were written here by the forward
+            else:
+                st = {'y': sv['y'], 'gates': sv['gates'], 'cells': sv['cells'], 'dy': torch.empty_like(dy),
+                      'dgx': torch.empty(B, T, 2, G * H, device=dev), 'dgh': torch.empty(B, T, 2, G * H, device=dev) if gru else None,
+                      'carry': torch.empty(2, B, H, device=dev), 'dg_cur': torch.empty(2, B, G * H, device=dev),
+                      'dh_rec': torch.empty(2, B, H, device=dev), 'whh': lw['whh'], 'graph': None}
+            st['dy'].copy_(dy)
+            if use_graph:
+                st['whh'].copy_(lw['whh'])
+            if use_graph and st['graph'] is not None:
+                st['graph'].replay()
+            else:
+                self._bptt_chain(cell, st, B, T, H)          # eager: also warms cuBLAS up before any capture
+                if use_graph and T > 4:
+                    # the chain is launch bound (2 launches per time step): capture it once, replay it from now on
+                    cur = torch.cuda.current_stream()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(cur)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(graph, stream=side):
+                            self._bptt_chain(cell, st, B, T, H)
+                    cur.wait_stream(side)
+                    st['graph'] = graph
+            dgx, dgh = st['dgx'], st['dgh']
             x2d = sv['x'].reshape(B * T, -1)
             dgx2d = dgx.view(B * T, 2 * G * H)
             dW_ih = dgx2d.t() @ x2d                                              # [2*G*H, in]
