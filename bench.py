@@ -215,25 +215,37 @@ def stage_times(sep, wav, idx, reps=3):
             ws = M.recurrent_workspace(B, T, H, cell, tc_rec, x.device)
             xproj = torch.empty(B * T, 2 * G * H, device=x.device)
             inp = x
-            for lw in packed.get():
+            layers = packed.get()
+            fuse = tc_rec and M.use_tensor_cores()
+            planes = hmean = None
+            Kpy = (2 * H + 63) // 64 * 64
+            for li, lw in enumerate(layers):       # the same sequence rnn_forward issues, with events between the halves
                 e0, e1, e2 = ev(), ev(), ev(); e0.record()
                 x2d = inp.view(B * T, -1)
                 if M.use_tensor_cores():
-                    M.linear_tc(M.split_bf16(x2d), M.weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H,
-                                x2d.shape[1], out=xproj)
+                    a_pl = planes if planes is not None else M.split_bf16(x2d)
+                    M.linear_tc(a_pl, M.weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
                 else:
                     M.linear_fwd(x2d, lw['wih'], lw['bias'], 'none', out=xproj)
                 e1.record()
-                y = M.recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec)
+                planes = None
+                last = li == len(layers) - 1
+                if fuse:
+                    planes = torch.empty(2, B * T, Kpy, device=x.device, dtype=torch.bfloat16)
+                    if Kpy > 2 * H:
+                        planes[:, :, 2 * H:].zero_()
+                    if last:
+                        hmean = torch.empty(B, 2 * H, device=x.device)
+                y = M.recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, None, None, None, planes, hmean if last else None)
                 e2.record(); torch.cuda.synchronize()
                 t['rnn_xproj'] += e0.elapsed_time(e1); t['rnn_recurrent'] += e1.elapsed_time(e2)
                 inp = y
             e0, e1 = ev(), ev(); e0.record()
-            q, _ = sep.queries(inp, idx)
+            q, _ = sep.queries(inp, idx, hmean)
             e1.record(); torch.cuda.synchronize(); t['query'] += e0.elapsed_time(e1)
             lin = sep.mix.Linear
             e0, e1 = ev(), ev(); e0.record()
-            masks = M.emb_attn_mask(inp, lin.weight, lin.bias, q, x.shape[2], W['E'])
+            masks = M.emb_attn_mask(inp, lin.weight, lin.bias, q, x.shape[2], W['E'], h_planes=planes)
             e1.record(); torch.cuda.synchronize(); t['emb_attn_mask'] += e0.elapsed_time(e1)
             e0, e1 = ev(), ev(); e0.record()
             features.mask_istft(masks, batch['mix_mag'], W['hop'])

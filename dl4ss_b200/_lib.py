@@ -34,7 +34,7 @@ SIGNATURES = {
     'dl4ss_rnn_tc_whh_bytes': (c_sz, [c_i]),
     'dl4ss_rnn_tc_pack_whh': (c_i, [c_i, c_p, c_i, c_p, c_p]),
     'dl4ss_rnn_tc_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
-    'dl4ss_rnn_layer_tc_fwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    'dl4ss_rnn_layer_tc_fwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     'dl4ss_emb_attn_mask_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'dl4ss_emb_attn_mask_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p,
                                       c_p, c_sz, c_p]),

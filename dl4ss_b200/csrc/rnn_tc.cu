@@ -50,6 +50,9 @@ struct RnnTcParams {
     float *y;                  // [B,T,2H]
     float *gates_save;         // [B,T,2,G*H] or null
     float *cell_save;          // [B,T,2,H] or null
+    __nv_bfloat16 *y_planes;   // optional [2 (hi,lo)][B*T][Kpy]: y pre-split for the next tensor-core projection
+    float *hmean_out;          // optional [B,2H]: mean over T of y (ADDJUST input)
+    int Kpy;
     __nv_bfloat16 *hbuf;       // [2 ping-pong][2 dir][2 plane][Bpad][Kp]
     unsigned *counters;        // [2][tiles_total]
     const __nv_bfloat16 *wplanes;   // packed W_hh planes [2][2 dir * 4H][Kp]
@@ -269,6 +272,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) bcol[i] = chalf * 16 + 4 * i + g;
             float state[4] = {0.f, 0.f, 0.f, 0.f};   // LSTM: c ; GRU: h
+            float hsum[4] = {0.f, 0.f, 0.f, 0.f};    // sum over t of this thread's cells (ADDJUST mean)
             const float bhn = (CELL == DL4SS_CELL_GRU && uvalid) ? __ldg(p.bhn + (size_t)dir * H + u) : 0.f;
 
             for (int s = 0; s < T; ++s) {
@@ -347,6 +351,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                 }
                 if (tr && lane == 0) stamp(p, s, 9);
                 // publish h_t first (the group's next step hangs on it); the fp32 outputs follow off the critical path
+                __nv_bfloat16 hhi[4], hlo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    hhi[i] = __float2bfloat16_rn(hnew[i]);
+                    hlo[i] = __float2bfloat16_rn(hnew[i] - __bfloat162float(hhi[i]));
+                    hsum[i] += hnew[i];
+                }
                 if (s + 1 < T) {
                     if (uvalid) {
                         const int pp = s & 1;
@@ -355,9 +366,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (row0 + bcol[i] < p.B) {
-                                const __nv_bfloat16 h0 = __float2bfloat16_rn(hnew[i]);
-                                hh[(size_t)bcol[i] * p.Kp] = h0;
-                                hl[(size_t)bcol[i] * p.Kp] = __float2bfloat16_rn(hnew[i] - __bfloat162float(h0));
+                                hh[(size_t)bcol[i] * p.Kp] = hhi[i];
+                                hl[(size_t)bcol[i] * p.Kp] = hlo[i];
                             }
                         }
                     }
@@ -376,6 +386,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                         const int b = row0 + bcol[i];
                         if (b < p.B) {
                             p.y[((size_t)b * T + t) * 2 * H + (size_t)dir * H + u] = hnew[i];
+                            if (p.y_planes != nullptr) {
+                                const size_t o = ((size_t)b * T + t) * p.Kpy + (size_t)dir * H + u;
+                                p.y_planes[o] = hhi[i];
+                                p.y_planes[(size_t)p.B * T * p.Kpy + o] = hlo[i];
+                            }
                             if (p.gates_save != nullptr) {
                                 float *go = p.gates_save + (((size_t)b * T + t) * 2 + dir) * GH + u;
 #pragma unroll
@@ -386,6 +401,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                         }
                     }
                 }
+            }
+            if (p.hmean_out != nullptr && uvalid) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (row0 + bcol[i] < p.B)
+                        p.hmean_out[(size_t)(row0 + bcol[i]) * 2 * H + (size_t)dir * H + u] = hsum[i] / (float)T;
             }
         }
     }
@@ -505,6 +526,7 @@ extern "C" size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell) {
 
 extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
                                       float *y, int B, int T, int H, float *gates_save, float *cell_save,
+                                      void *y_planes, float *hmean_out,
                                       void *workspace, size_t workspace_bytes, void *stream) {
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_tc_fwd: bad cell %d", cell);
     DL4SS_CHECK_ARG(xproj && whh_planes && y, "rnn_layer_tc_fwd: null operand");
@@ -526,6 +548,8 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
     DL4SS_CUDA(cudaMemsetAsync(workspace, 0, need, st));     // counters, and the zero k-padding / row padding of h
     RnnTcParams p;
     p.xproj = xproj; p.bhn = bhn; p.y = y; p.gates_save = gates_save; p.cell_save = cell_save;
+    p.y_planes = (__nv_bfloat16 *)y_planes; p.hmean_out = hmean_out;
+    p.Kpy = cdiv(2 * H, RT_KC) * RT_KC;
     p.B = B; p.T = T; p.H = H;
     p.nkc = cdiv(H, RT_KC);
     p.Kp = p.nkc * RT_KC;

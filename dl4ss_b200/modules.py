@@ -147,7 +147,7 @@ def whh_planes(lw, cell, H):
     return pl
 
 
-def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None, y=None):
+def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None, y=None, y_planes=None, hmean=None):
     """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]."""
     lib = _lib.load()
     if y is None:
@@ -155,6 +155,7 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     if tc_rec:
         rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(whh_planes(lw, cell, H), torch.bfloat16),
                                         _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                        _lib.ptr(y_planes, torch.bfloat16), _lib.ptr(hmean),
                                         _lib.ptr(ws, torch.uint8), ws.numel(), _lib.stream())
         _lib.check(rc, 'dl4ss_rnn_layer_tc_fwd')
     else:
@@ -165,10 +166,12 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     return y
 
 
-def rnn_forward(packed, x, save=None, buffers=None):
+def rnn_forward(packed, x, save=None, buffers=None, extras=None):
     """Bidirectional multi-layer LSTM/GRU forward, batch_first, zero initial state.
     x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward; `buffers` (list of dicts
-    with 'y', 'gates', 'cells' per layer) makes the layers write into caller-owned static tensors."""
+    with 'y', 'gates', 'cells' per layer) makes the layers write into caller-owned static tensors; `extras` (dict)
+    receives what the last layer's kernel produced on the side: 'planes' (its output as bf16 hi/lo planes, ready
+    for the next tensor-core projection) and 'hmean' (its mean over T), or None when the fp32 kernels ran."""
     lib = _lib.load()
     rnn = packed.rnn
     gru = isinstance(rnn, nn.GRU)
@@ -181,10 +184,16 @@ def rnn_forward(packed, x, save=None, buffers=None):
     ws = recurrent_workspace(B, T, H, cell, tc_rec, dev)
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
-    for li, lw in enumerate(packed.get()):
+    layers = packed.get()
+    fuse = tc_rec and use_tensor_cores()        # K3 emits its output pre-split for the next projection (+ the T-mean)
+    planes = None                               # bf16 hi/lo planes of `inp`, when the producer made them
+    hmean = None
+    Kpy = (2 * H + 63) // 64 * 64
+    for li, lw in enumerate(layers):
         if use_tensor_cores():
             x2d = inp.view(B * T, -1)
-            linear_tc(split_bf16(x2d), weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
+            a_pl = planes if planes is not None else split_bf16(x2d)
+            linear_tc(a_pl, weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
         else:
             linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
         gates = cells = y_out = None
@@ -193,14 +202,25 @@ def rnn_forward(packed, x, save=None, buffers=None):
         elif save is not None:
             gates = torch.empty(B, T, 2, G * H, device=dev, dtype=torch.float32)
             cells = torch.empty(B, T, 2, H, device=dev, dtype=torch.float32)
-        y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells, y_out)
+        planes = None
+        if fuse:
+            planes = torch.empty(2, B * T, Kpy, device=dev, dtype=torch.bfloat16)
+            if Kpy > 2 * H:
+                planes[:, :, 2 * H:].zero_()    # the kernel writes columns [0, 2H)
+            if li == len(layers) - 1:
+                hmean = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
+        y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells, y_out, planes,
+                            hmean if li == len(layers) - 1 else None)
         if save is not None:
             save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
         inp = y
+    if extras is not None:
+        extras['planes'] = planes
+        extras['hmean'] = hmean
     return inp
 
 
-def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=True):
+def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=True, h_planes=None):
     """Fused Linear+tanh -> dot attention -> masks (K4).
     h [B,T,K], weight [F*E,K], bias [F*E], query [B,S,E|2E] -> [B,S,T,F] (or [B,S,T,F,2])."""
     lib = _lib.load()
@@ -214,7 +234,7 @@ def emb_attn_mask(h, weight, bias, query, F, E, complex_mask=False, decompress=T
         # keep both plane tensors referenced until the launch is queued: a temporary freed between two argument
         # expressions can be handed to the next allocation (e.g. the first-use weight split) and overwritten
         w_pl = weight_planes(weight)
-        h_pl = split_bf16(h.view(B * T, K))
+        h_pl = h_planes if h_planes is not None else split_bf16(h.view(B * T, K))
         rc = lib.dl4ss_emb_attn_mask_tc_fwd(_lib.ptr(h_pl, torch.bfloat16),
                                             _lib.ptr(w_pl, torch.bfloat16),
                                             _lib.ptr(bias, name='bias'), _lib.ptr(query, name='query'),
@@ -325,8 +345,8 @@ class MIX_SPEECH(nn.Module):
         self.Linear = nn.Linear(2 * config.HIDDEN_UNITS, self.input_fre * config.EMBEDDING_SIZE)
         self._packed = _PackedRNN(self.layer)
 
-    def encode(self, x):
-        return rnn_forward(self._packed, x)
+    def encode(self, x, extras=None):
+        return rnn_forward(self._packed, x, extras=extras)
 
     def forward(self, x):
         B, T, F = x.shape

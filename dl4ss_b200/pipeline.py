@@ -35,22 +35,27 @@ class Separator(object):
     def features(self, mix_wav):
         return features.prepare_batch(mix_wav, self.n_fft, self.hop, self.log_spectral)
 
-    def queries(self, hidden, spk_idx):
+    def queries(self, hidden, spk_idx, hmean=None):
+        """Speaker queries [B,S,E|2E]; `hmean` [B,2H] (the encoder kernel's fused T-mean) replaces the pass over
+        `hidden` that ADDJUST's mean needs."""
         idx = self.emb.index_tensor(spk_idx)
         wadj = self.adj.layer.weight.detach() if self.adj is not None else None
-        q, err = M._speaker_query(hidden if wadj is not None else None, self.emb.layer.weight.detach(), idx,
-                                  wadj, 1)
+        h = None
+        if wadj is not None:
+            h = hmean.unsqueeze(1) if hmean is not None else hidden
+        q, err = M._speaker_query(h, self.emb.layer.weight.detach(), idx, wadj, 1)
         return q, err
 
     def masks(self, mix_feas, spk_idx, check_index=True):
         """mix_feas [B,T,F], spk_idx int [B,S] -> masks [B,S,T,F] (cRM: decompressed [B,S,T,F,2])."""
         B, T, F = mix_feas.shape
-        hidden = self.mix.encode(mix_feas)
-        q, err = self.queries(hidden, spk_idx)
+        extras = {}
+        hidden = self.mix.encode(mix_feas, extras)
+        q, err = self.queries(hidden, spk_idx, extras.get('hmean'))
         lin = self.mix.Linear
         E = lin.out_features // F
         out = M.emb_attn_mask(hidden, lin.weight, lin.bias, q, F, E,
-                              complex_mask=self.complex_mask, decompress=True)
+                              complex_mask=self.complex_mask, decompress=True, h_planes=extras.get('planes'))
         if check_index and int(err.item()):
             raise IndexError('index out of range in self')
         return out

@@ -118,8 +118,13 @@ void   dl4ss_rnn_tc_set_trace(void *dev_buf, int steps);
 size_t dl4ss_rnn_tc_whh_bytes(int H);
 int    dl4ss_rnn_tc_pack_whh(int cell, const float *whh, int H, void *planes, void *stream);
 size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
+/* Optional fused outputs (NULL to skip): y_planes = y already split into bf16 hi/lo planes
+ * [2][B*T][Kp], Kp = 2H rounded up to 64, for the next dl4ss_linear_tc_fwd / dl4ss_emb_attn_mask_tc_fwd (the
+ * kernel writes columns [0,2H); the caller keeps the padding columns zero); hmean_out [B,2H] = mean over T of
+ * y, the ADDJUST input (pass it to dl4ss_speaker_query_fwd as h with T = 1). */
 int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
                            float *y, int B, int T, int H, float *gates_save, float *cell_save,
+                           void *y_planes, float *hmean_out,
                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- K4: Linear + tanh + speaker attention + mask, fused ---------------------------------
