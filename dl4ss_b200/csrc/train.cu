@@ -249,3 +249,73 @@ extern "C" int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float 
     DL4SS_LAUNCH_CHECK("rnn_bwd_step_kernel");
     return DL4SS_OK;
 }
+
+// ----------------------------------------------------------------------------------------- a1: mixture synthesis
+// The per-source waveform preprocessing of the reference generators, batched on the GPU
+// (TDAA_beta/predata_fromList.py:140-177 ; Torch_multi/predata_multiAims.py:144-177):
+//   x = x[:n] ; x -= mean(x) ; x /= max|x| ; zero-pad to L ; x *= 10^(dB/20) ; mix = sum_s x_s
+// One CTA per utterance; three passes over each source (sum, max|x-mean|, write).
+namespace dl4ss {
+__device__ __forceinline__ float block_reduce(float v, float *red, bool is_max) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, w) : v + w;
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = is_max ? 0.f : 0.f;
+    for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(512)
+premix_kernel(const float *__restrict__ src, const int *__restrict__ lengths, const float *__restrict__ gains_db,
+              int S, int L, float *__restrict__ src_out, float *__restrict__ mix_out) {
+    __shared__ float red[32];
+    __shared__ float sc_mean[16], sc_scale[16];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int s = 0; s < S; ++s) {
+        const float *x = src + ((size_t)b * S + s) * L;
+        int n = lengths ? lengths[b * S + s] : L;
+        n = n < 0 ? 0 : (n > L ? L : n);
+        double acc = 0.0;                                   // the reference works in float64
+        for (int i = tid; i < n; i += blockDim.x) acc += (double)x[i];
+        // reduce the double sum through two floats (hi + lo) to reuse the float reducer
+        const float hi = (float)acc, lo = (float)(acc - (double)hi);
+        const float shi = block_reduce(hi, red, false), slo = block_reduce(lo, red, false);
+        const float mean = n > 0 ? (float)(((double)shi + (double)slo) / (double)n) : 0.f;
+        float mx = 0.f;
+        for (int i = tid; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(x[i] - mean));
+        mx = block_reduce(mx, red, true);
+        if (tid == 0) {
+            sc_mean[s] = mean;
+            sc_scale[s] = (mx > 0.f ? 1.0f / mx : 0.f) * exp10f(gains_db[b * S + s] * 0.05f);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < L; i += blockDim.x) {
+        float m = 0.f;
+        for (int s = 0; s < S; ++s) {
+            int n = lengths ? lengths[b * S + s] : L;
+            const size_t o = ((size_t)b * S + s) * L + i;
+            const float v = (i < n) ? (src[o] - sc_mean[s]) * sc_scale[s] : 0.f;
+            if (src_out) src_out[o] = v;
+            m += v;
+        }
+        mix_out[(size_t)b * L + i] = m;
+    }
+}
+}  // namespace dl4ss
+
+extern "C" int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
+                                float *src_out, float *mix_out, void *stream) {
+    if (B == 0) return DL4SS_OK;
+    DL4SS_CHECK_ARG(src && gains_db && mix_out, "premix_fwd: null operand");
+    DL4SS_CHECK_ARG(B >= 0 && S >= 1 && S <= 16 && L >= 1, "premix_fwd: bad B/S/L %d/%d/%d (S <= 16)", B, S, L);
+    premix_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(src, lengths, gains_db, S, L, src_out, mix_out);
+    DL4SS_LAUNCH_CHECK("premix_kernel");
+    return DL4SS_OK;
+}

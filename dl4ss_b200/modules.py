@@ -479,14 +479,11 @@ class ADDJUST(nn.Module):
 
 
 def top_k_mask(batch_pro, alpha, top_k):
-    """Host-side speaker selection, as in the reference (python loops over B; boundary glue)."""
-    size = batch_pro.size()
-    final = torch.zeros(size)
-    sort_result, sort_index = torch.sort(batch_pro.detach().cpu(), 1, True)
-    sort_index = sort_index[:, :top_k]
-    sort_result = torch.sum(sort_result > alpha, 1)
-    for line_idx in range(size[0]):
-        line_top_k = sort_index[line_idx][:int(sort_result[line_idx])]
-        for i in line_top_k.numpy():
-            final[line_idx, i] = 1
+    """Speaker selection (TDAA_beta/main_run_sstune_EvalVer.py:390-405): per row, the (at most) `top_k` most
+    probable speakers whose probability exceeds `alpha`, as a 0/1 matrix.  Same result as the reference's
+    python loops, evaluated with tensor ops on the device `batch_pro` lives on."""
+    vals, index = torch.sort(batch_pro.detach(), 1, True)
+    keep = (vals[:, :top_k] > alpha).to(torch.float32)
+    final = torch.zeros(batch_pro.size(), device=batch_pro.device, dtype=torch.float32)
+    final.scatter_(1, index[:, :top_k], keep)
     return final

@@ -184,6 +184,14 @@ int dl4ss_speaker_query_fwd(const float *h, int B, int T, int C, const float *ta
 int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
                         int B, int S, int TF, double *loss_out, void *stream);
 
+/* ---- a1: batched mixture synthesis ---------------------------------------------------------
+ * The per-source preprocessing of the reference generators (TDAA_beta/predata_fromList.py:140-177):
+ * crop to lengths[b,s] (NULL: L), subtract the mean, divide by max|.|, zero-pad to L, gain 10^(dB/20),
+ * mixture = sum over sources.  src [B,S,L] fp32 ; gains_db [B,S] ; src_out [B,S,L] (may be NULL, may alias
+ * src) ; mix_out [B,L].  S <= 16. */
+int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
+                     float *src_out, float *mix_out, void *stream);
+
 /* ---- training step, backward side -----------------------------------------------------------
  * loss = l0 + 0.5*l1 (real; EvalVer.py:641,659-666) or l_re + l_im (cRM; cRM_EvalVer.py:741-743).
  * dl4ss_mask_loss_bwd: dmask = d(loss)/d(mask), same layout as mask.

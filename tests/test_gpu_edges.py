@@ -106,3 +106,27 @@ def test_errors_are_loud(cuda):
         d.mask_istft(torch.zeros(1, 2, 5, 129, device=cuda), torch.zeros(1, 6, 129, 2, device=cuda), 128)
     with pytest.raises(RuntimeError):
         d.linear_fwd(torch.zeros(2, 3, device=cuda).t(), torch.zeros(4, 2, device=cuda))   # non-contiguous
+
+
+def test_premix_matches_reference_preprocessing(cuda):
+    """a1: crop / -mean / /max|.| / zero-pad / dB gain / sum, against the float64 oracle."""
+    import dl4ss_b200 as d
+    from oracle import stft_ref as sr
+    rng = np.random.RandomState(0)
+    B, S, L = 3, 3, 9000
+    lengths = rng.randint(2000, L + 1, (B, S)); lengths[0, 0] = L
+    gains = rng.uniform(-2.5, 2.5, (B, S))
+    raw = np.zeros((B, S, L), np.float32)
+    for b in range(B):
+        for s in range(S):
+            raw[b, s, :lengths[b, s]] = (rng.standard_normal(lengths[b, s]) * rng.uniform(0.1, 3) + rng.uniform(-1, 1)).astype(np.float32)
+    ref = np.array([[sr.preprocess_source(raw[b, s, :lengths[b, s]].astype(np.float64), L, gains[b, s]) for s in range(S)] for b in range(B)])
+    out = d.premix(torch.from_numpy(raw).cuda(), torch.from_numpy(gains), torch.from_numpy(lengths))
+    assert np.abs(out['sources'].cpu().numpy() - ref).max() < 2e-6 * np.abs(ref).max()
+    assert np.abs(out['mix_wav'].cpu().numpy() - ref.sum(1)).max() < 4e-6 * np.abs(ref).max()
+    assert torch.all(out['sources'][1, 1, int(lengths[1, 1]):] == 0)
+    # feeds K1 directly: features of the GPU mixture == oracle features of the oracle mixture
+    batch = d.prepare_batch(out['mix_wav'], sources=out['sources'])
+    f_ref = np.stack([sr.features_ref(m, 256, 128)['mix_feas'] for m in ref.sum(1)])
+    assert rel_err(batch['mix_feas'].cpu().numpy(), f_ref) < 1e-4
+    assert tuple(batch['multi_spk_fea'].shape) == (B, S, 1 + L // 128, 129)
