@@ -78,7 +78,7 @@ __device__ __forceinline__ void red_relaxed_gpu_add(unsigned *p, unsigned v) {
 __device__ __forceinline__ void stamp(const RnnTcParams &p, int s, int slot) {
     if (p.trace != nullptr && blockIdx.x == 0 && s < p.trace_steps) p.trace[s * 16 + slot] = clock64();
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 
 // branch-free select (selp): a chain of ?: on a lane-dependent index compiles to divergent branches
 __device__ __forceinline__ float selp_f(float a, float b, int pick_a) {
