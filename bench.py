@@ -487,7 +487,7 @@ def main():
     Lout = W['hop'] * (W['L'] // W['hop'])
     h_outs = [torch.empty(B, W['S'], Lout, dtype=torch.float32).pin_memory() for _ in range(3)]
     pipe = d.HostPipeline(sep, B, W['L'], W['S'], depth=2, device=device)
-    for i in range(3):
+    for i in range(max(8, args.warmup)):      # also lets the PCIe link leave its idle (down-trained) state
         pipe.submit(h_in[i % 4], h_idx, h_outs[i % 3])
     pipe.drain()
     barrier()
