@@ -50,3 +50,7 @@ RNN_TENSOR_CORES = True
 # Not in the reference: the training step keeps static per-layer buffers and replays the T-step BPTT chain
 # (launch bound: one library GEMM + one gate kernel per time step) from a CUDA graph captured on first use.
 TRAIN_CUDA_GRAPHS = True
+
+# Not in the reference: run the dense contractions of the backward pass (dW = dY^T X, dX = dY W) on the tcgen05
+# bf16x3 projection kernel; False leaves them to the library GEMM (cuBLAS fp32).
+TRAIN_TC_GEMMS = True

@@ -61,6 +61,32 @@ split_bf16_kernel(const float *__restrict__ x, int ld, long long R, int K, int K
     }
 }
 
+// transposing split: fp32 x[R, C] -> bf16 planes [2][C][Rp] (Rp = R rounded up to 64, zero padded): the K-major
+// operand form of x^T, for the contractions over the row dimension of the backward pass (dW = dY^T * X)
+__global__ void __launch_bounds__(256)
+split_bf16_t_kernel(const float *__restrict__ x, long long ld, int R, int C, int Rp, __nv_bfloat16 *__restrict__ planes) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        tile[ty + 8 * i][tx] = (r < R && c < C) ? x[(size_t)r * ld + c] : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16 *hi = planes, *lo = planes + (size_t)C * Rp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (c < C && r < Rp) {
+            const float v = tile[tx][ty + 8 * i];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hi[(size_t)c * Rp + r] = h;
+            lo[(size_t)c * Rp + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ epilogues
 template <int ACT>          // DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID, compile time: the epilogue is on the critical path
 struct EpiPlain {
@@ -380,6 +406,19 @@ extern "C" int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void
     if (blocks > cap) blocks = cap;
     split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, R, K, Kp, (__nv_bfloat16 *)planes);
     DL4SS_LAUNCH_CHECK("split_bf16_kernel");
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_split_bf16_t(const float *x, long long ld, int R, int C, void *planes, void *stream) {
+    if (R == 0 || C == 0) return DL4SS_OK;
+    DL4SS_CHECK_ARG(x && planes, "split_bf16_t: null operand");
+    DL4SS_CHECK_ARG(R >= 1 && C >= 1 && ld >= C, "split_bf16_t: bad R/C/ld %d/%d/%lld", R, C, ld);
+    DL4SS_CHECK_ARG((((uintptr_t)planes) & 15) == 0, "split_bf16_t: planes must be 16-byte aligned");
+    const int Rp = (R + TBK - 1) / TBK * TBK;
+    dim3 grid(cdiv(C, 32), Rp / 32);
+    DL4SS_CHECK_ARG(grid.y < 65536, "split_bf16_t: too many rows");
+    split_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, R, C, Rp, (__nv_bfloat16 *)planes);
+    DL4SS_LAUNCH_CHECK("split_bf16_t_kernel");
     return DL4SS_OK;
 }
 

@@ -53,6 +53,40 @@ def split_bf16(x2d):
     return planes
 
 
+def split_bf16_t(x2d):
+    """fp32 [R,C] -> bf16 hi/lo planes of the TRANSPOSE, [2,C,Rp] (Rp = R rounded up to 64, zero padded)."""
+    lib = _lib.load()
+    R, C = x2d.shape
+    Rp = (R + 63) // 64 * 64
+    planes = torch.empty(2, C, Rp, device=x2d.device, dtype=torch.bfloat16)
+    if x2d.stride(1) != 1 or x2d.dtype != torch.float32:
+        x2d = x2d.contiguous().float()
+    rc = lib.dl4ss_split_bf16_t(ctypes_ptr(x2d), x2d.stride(0), R, C,
+                                _lib.ptr(planes, torch.bfloat16), _lib.stream())
+    _lib.check(rc, 'dl4ss_split_bf16_t')
+    return planes
+
+
+def ctypes_ptr(t):
+    """Device pointer of a row-strided (inner stride 1) CUDA fp32 tensor."""
+    import ctypes
+    if not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1:
+        raise RuntimeError('dl4ss_b200: need a CUDA float32 tensor with unit inner stride')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def matmul_tn(a2d, b2d):
+    """a2d^T @ b2d  ([R,Ca],[R,Cb] -> [Ca,Cb]) on tcgen05 (bf16x3): both operands transposed-split, contraction over R."""
+    R = a2d.shape[0]
+    return linear_tc(split_bf16_t(a2d), split_bf16_t(b2d), None, a2d.shape[1], b2d.shape[1], R)
+
+
+def matmul_nn(a2d, w):
+    """a2d @ w  ([M,K],[K,N] -> [M,N]) on tcgen05 (bf16x3): w is transposed once into the kernel's [N,K] operand form."""
+    a2d = a2d if a2d.is_contiguous() else a2d.contiguous()
+    return linear_tc(split_bf16(a2d), split_bf16(w.t().contiguous()), None, a2d.shape[0], w.shape[1], a2d.shape[1])
+
+
 def weight_planes(w):
     """bf16 planes of a weight matrix, cached ON the tensor object and re-split only when the
     parameter is modified in place (optimizer step, load_state_dict) or moved."""

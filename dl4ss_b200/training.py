@@ -8,9 +8,10 @@ Mirrors one iteration of the reference's training loop
 without the discriminator terms (out of scope).  The forward runs the same CUDA kernels
 as inference (tcgen05 projections, persistent recurrent kernel) with the gate activations saved; the
 backward is written out by hand: fused CUDA kernels for the loss / attention / BPTT gate arithmetic
-(csrc/train.cu) and plain library GEMMs (torch.matmul -> cuBLAS fp32) for the dense contractions
-dW, dx, dh and the per-step dh_rec = dgates x W_hh.  Gradients land in the parameters' `.grad`, so any
-torch optimizer (the reference uses Adam, lr 2e-4) steps them.
+(csrc/train.cu), the tcgen05 bf16x3 projection kernel for the dense contractions dW = dY^T X (operands through
+the transposing split dl4ss_split_bf16_t) and dX = dY W, and a plain library GEMM (torch.bmm -> cuBLAS fp32)
+only for the tiny per-step dh_rec = dgates x W_hh of the BPTT chain.  Gradients land in the parameters'
+`.grad`, so any torch optimizer (the reference uses Adam, lr 2e-4) steps them.
 
 Utterances shard by batch across ranks: every rank runs the step on its shard with the
 loss normalised by the GLOBAL element count, then one all-reduce (sum) of the flat fp32 gradient
@@ -69,6 +70,19 @@ def allreduce_gradients(params, group=None):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     unflatten_grads(flat, params)
     return flat.numel() * 4
+
+
+def _mm_tn(a2d, b2d):
+    """a^T b (contraction over rows): tcgen05 bf16x3 when the tensor-core path is on, else the library GEMM."""
+    if M.use_tensor_cores() and config.TRAIN_TC_GEMMS:
+        return M.matmul_tn(a2d, b2d)
+    return a2d.t() @ b2d
+
+
+def _mm_nn(a2d, w):
+    if M.use_tensor_cores() and config.TRAIN_TC_GEMMS:
+        return M.matmul_nn(a2d, w)
+    return a2d @ w
 
 
 def _accum(p, g):
@@ -186,9 +200,9 @@ class TrainStep(object):
         dz = emb.view(B * T, F * E)
         lin = self.mix.Linear
         h2d = hidden.view(B * T, -1)
-        _accum(lin.weight, dz.t() @ h2d)
+        _accum(lin.weight, _mm_tn(dz, h2d))
         _accum(lin.bias, dz.sum(0))
-        dh = (dz @ lin.weight.detach()).view(B, T, -1)
+        dh = _mm_nn(dz, lin.weight.detach()).view(B, T, -1)
         # speaker query backward (tiny: glue in torch)
         table = self.emb.layer.weight
         if self.adj is not None:
@@ -274,7 +288,7 @@ class TrainStep(object):
             dgx, dgh = st['dgx'], st['dgh']
             x2d = sv['x'].reshape(B * T, -1)
             dgx2d = dgx.view(B * T, 2 * G * H)
-            dW_ih = dgx2d.t() @ x2d                                              # [2*G*H, in]
+            dW_ih = _mm_tn(dgx2d, x2d)                                           # [2*G*H, in]
             db_x = dgx2d.sum(0)
             dgr = dgh if gru else dgx                                            # recurrent-side gate grads
             y = sv['y']
@@ -287,10 +301,10 @@ class TrainStep(object):
                 else:            # the reverse direction came from t+1
                     dg_t, h_prev = dgr[:, :-1, 1, :], y[:, 1:, H:]
                 _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)),
-                       dg_t.reshape(-1, G * H).t() @ h_prev.reshape(-1, H))
+                       _mm_tn(dg_t.reshape(-1, G * H), h_prev.reshape(-1, H)))
                 _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
             if l > 0:
-                dy = (dgx2d @ lw['wih']).view(B, T, -1).contiguous()
+                dy = _mm_nn(dgx2d, lw['wih']).view(B, T, -1).contiguous()
 
     # ------------------------------------------------------------------------------ full step
     def step(self, optimizer, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, group=None):

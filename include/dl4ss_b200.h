@@ -150,6 +150,9 @@ int dl4ss_emb_attn_mask_fwd(const float *h, const float *W, const float *bias, c
  * anything else returns DL4SS_EUNSUPPORTED and the caller uses dl4ss_emb_attn_mask_fwd. */
 size_t dl4ss_split_bf16_bytes(long long R, int K);
 int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, void *stream);
+/* transposing split: x [R,C] fp32 -> planes [2][C][Rp] of x^T (Rp = R rounded up to 64, zero padded,
+ * dl4ss_split_bf16_bytes(C, R) bytes): the operand form for contractions over the row dimension (dW = dY^T X). */
+int dl4ss_split_bf16_t(const float *x, long long ld, int R, int C, void *planes, void *stream);
 int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
                         int ldc, int M, int N, int K, int act, void *stream);
 int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
