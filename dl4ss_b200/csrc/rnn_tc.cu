@@ -43,6 +43,8 @@ constexpr int RT_THREADS = 512;
 constexpr int RT_WBLK = RT_ROWS * 128;         // bytes of one (k-chunk, plane) W block
 constexpr int RT_HBLK = RT_NT * 128;           // bytes of one (k-chunk, plane) h block
 constexpr int RT_XTILE = RT_NT * RT_XP;        // floats of one xproj buffer
+constexpr int RT_CTR_STRIDE = 64;              // uints between group counters: one 256-byte line each (atomics and the
+                                               // pollers of different groups must not share an L2 line)
 
 struct RnnTcParams {
     const float *xproj;        // [B,T,2,G*H]
@@ -128,7 +130,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
     const int u0 = slice * RT_HS;
     const int T = p.T, H = p.H;
     const size_t GH = (size_t)G * H;
-    unsigned *counters = p.counters + dir * p.tiles_total + tile_first;
+    unsigned *counters = p.counters + (size_t)(dir * p.tiles_total + tile_first) * RT_CTR_STRIDE;
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_h) : "memory");
@@ -175,7 +177,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                 for (int tl = 0; tl < nt; ++tl) {
                     const unsigned want = per_step * (unsigned)s;
                     if (tl == 0) stamp(p, s, 0);
-                    while (ld_acquire_gpu(counters + tl) < want) { }
+                    while (ld_acquire_gpu(counters + tl * RT_CTR_STRIDE) < want) { }
                     if (tl == 0) stamp(p, s, 1);
                     fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
                     unsigned char *hs = Hsm + (size_t)tl * nkc * 2 * RT_HBLK;
@@ -270,7 +272,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
             const int u = u0 + ul;
             const int row0 = (tile_first + tl) * RT_NT;
             const uint32_t taddr = tmem_base + ((uint32_t)(sp * 32) << 16) + tl * RT_TCOLS + chalf * 16;
-            unsigned *counter = counters + tl;
+            unsigned *counter = counters + tl * RT_CTR_STRIDE;
             const bool tr = (blockIdx.x == 0 && warp == 0);      // traced warp
             int bcol[4];                             // my 4 cells: utterance columns 16*chalf + 4*i + g
 #pragma unroll
@@ -524,7 +526,7 @@ extern "C" size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell) {
     if (B <= 0 || H <= 0) return 256;
     const size_t Bpad = (size_t)cdiv(B, RT_NT) * RT_NT;
     const size_t Kp = (size_t)cdiv(H, RT_KC) * RT_KC;
-    const size_t ctr = ((size_t)2 * (Bpad / RT_NT) * sizeof(unsigned) + 255) / 256 * 256;
+    const size_t ctr = (size_t)2 * (Bpad / RT_NT) * RT_CTR_STRIDE * sizeof(unsigned);
     return ctr + 8 * Bpad * Kp * sizeof(__nv_bfloat16);
 }
 
@@ -561,7 +563,7 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
     p.tiles_total = p.Bpad / RT_NT;
     p.nslices = H / RT_HS;
     p.counters = (unsigned *)workspace;
-    const size_t ctr = ((size_t)2 * p.tiles_total * sizeof(unsigned) + 255) / 256 * 256;
+    const size_t ctr = (size_t)2 * p.tiles_total * RT_CTR_STRIDE * sizeof(unsigned);
     p.hbuf = (__nv_bfloat16 *)((unsigned char *)workspace + ctr);
     p.ntiles = p.tpg = p.ngroups = 0;
     p.trace = g_trace; p.trace_steps = g_trace_steps;
