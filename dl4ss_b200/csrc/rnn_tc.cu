@@ -177,7 +177,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                 for (int tl = 0; tl < nt; ++tl) {
                     const unsigned want = per_step * (unsigned)s;
                     if (tl == 0) stamp(p, s, 0);
-                    while (ld_acquire_gpu(counters + tl * RT_CTR_STRIDE) < want) { }
+                    while (ld_acquire_gpu(counters + tl * RT_CTR_STRIDE) < want) { __nanosleep(40); }
                     if (tl == 0) stamp(p, s, 1);
                     fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
                     unsigned char *hs = Hsm + (size_t)tl * nkc * 2 * RT_HBLK;
