@@ -528,8 +528,9 @@ def main():
         roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
                 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
                 'traffic': tr['bytes_per_launch'] if tr else None, 'traffic_source': tr['source'] if tr else None,
-                'algorithmic_bytes_per_launch': (B * (1 + W['L'] // W['hop']) * 2 * (4 if W['cell'] == 'lstm' else 3) * W['H'] * 4
-                                                 + B * (1 + W['L'] // W['hop']) * 2 * W['H'] * 4) if dom == 'rnn_recurrent' else None,
+                # K3 per launch: reads xproj [B,T,2,G*H] fp32, writes y [B,T,2H] fp32 and its bf16 hi/lo planes [2][B*T][Kp]
+                'algorithmic_bytes_per_launch': (B * (1 + W['L'] // W['hop']) * (2 * (4 if W['cell'] == 'lstm' else 3) * W['H'] * 4
+                                                 + 2 * W['H'] * 4 + 2 * ((2 * W['H'] + 63) // 64 * 64) * 2)) if dom == 'rnn_recurrent' else None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
                 'launches_per_step': n_launch, 'ms_per_step': st[dom],
                 'note': 'algorithmic fp32 FLOPs; every tensor-core stage runs bf16x3 (3 MMA products per fp32 product); the recurrent stage is a latency chain of T sequential steps per layer, not throughput bound (DESIGN.md 4)'}
