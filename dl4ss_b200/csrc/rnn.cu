@@ -315,9 +315,13 @@ static int launch_rnn(RnnParams p, int nchunk_rows, cudaStream_t st, int *launch
 
 template <int CELL>
 static int rnn_dispatch(RnnParams p, int rows_left, cudaStream_t st, int *launched_rows) {
-    if (rows_left > 32) return launch_rnn<CELL, 10, 2, 2, 32>(p, rows_left, st, launched_rows);
-    if (rows_left > 8) return launch_rnn<CELL, 10, 2, 1, 32>(p, rows_left, st, launched_rows);
-    return launch_rnn<CELL, 5, 2, 1, 8>(p, rows_left, st, launched_rows);
+    // largest batch tile first; a configuration whose resident W_hh slice + h tile does not fit in shared memory
+    // (H = 600: the speaker classifier) falls through to the next smaller one
+    int rc = DL4SS_EUNSUPPORTED;
+    if (rows_left > 32) rc = launch_rnn<CELL, 10, 2, 2, 32>(p, rows_left, st, launched_rows);
+    if (rc == DL4SS_EUNSUPPORTED && rows_left > 8) rc = launch_rnn<CELL, 10, 2, 1, 32>(p, rows_left, st, launched_rows);
+    if (rc == DL4SS_EUNSUPPORTED) rc = launch_rnn<CELL, 5, 2, 1, 8>(p, rows_left, st, launched_rows);
+    return rc;
 }
 
 }  // namespace dl4ss

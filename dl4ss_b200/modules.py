@@ -394,6 +394,31 @@ class MIX_SPEECH(nn.Module):
         return (out, xx) if self.return_hidden else out
 
 
+class MIX_SPEECH_classifier(nn.Module):
+    """MIX_SPEECH_classifier(input_fre, mix_speech_len, num_labels).forward(x[B,T,F]) -> speaker probabilities
+    [B,num_labels]: BLSTM 3 x (2*HIDDEN_UNITS) -> mean over T -> Linear -> sigmoid
+    (TDAA_beta/main_run_sstune_EvalVer.py:305-326).  The step before the separation path at
+    inference: `top_k_mask` of its output picks the speakers to extract.  H = 600 is outside the tcgen05 recurrent
+    kernel's range (W_hh would need 600 TMEM columns per plane), so the layers run on the fp32 persistent kernel."""
+
+    def __init__(self, input_fre, mix_speech_len, num_labels):
+        super(MIX_SPEECH_classifier, self).__init__()
+        self.input_fre = input_fre
+        self.mix_speech_len = mix_speech_len
+        self.layer = nn.LSTM(input_size=input_fre, hidden_size=2 * config.HIDDEN_UNITS, num_layers=3,
+                             batch_first=True, bidirectional=True)
+        self.Linear = nn.Linear(2 * 2 * config.HIDDEN_UNITS, num_labels)
+        self._packed = _PackedRNN(self.layer)
+
+    def forward(self, x):
+        extras = {}
+        y = rnn_forward(self._packed, x, extras=extras)
+        m = extras.get('hmean')
+        if m is None:
+            m = y.mean(1)                      # [B, 4*HIDDEN_UNITS]
+        return linear_fwd(m.contiguous(), self.Linear.weight.detach(), self.Linear.bias.detach(), 'sigmoid')
+
+
 class ATTENTION(nn.Module):
     """ATTENTION(hidden_size, mode='dot'|'align').forward(mix_hidden[N,T,F,E], query[N,E|2E]).
 

@@ -65,6 +65,25 @@ class MIX_SPEECH(nn.Module):
         return out, xx
 
 
+class MIX_SPEECH_classifier(nn.Module):
+    """Speaker-presence classifier ("who is talking"): BLSTM 3 x (2*HIDDEN_UNITS) -> mean over T -> Linear -> sigmoid
+    (TDAA_beta/main_run_sstune_EvalVer.py:305-326).  Its top-k speakers are the queries of the separation path."""
+
+    def __init__(self, config, input_fre, mix_speech_len, num_labels):
+        super(MIX_SPEECH_classifier, self).__init__()
+        self.input_fre = input_fre
+        self.mix_speech_len = mix_speech_len
+        self.layer = nn.LSTM(input_size=input_fre, hidden_size=2 * config.HIDDEN_UNITS, num_layers=3,
+                             batch_first=True, bidirectional=True)
+        self.Linear = nn.Linear(2 * 2 * config.HIDDEN_UNITS, num_labels)
+
+    def forward(self, x):
+        x, hidden = self.layer(x)
+        x = x.contiguous()
+        x = torch.mean(x, 1)
+        return torch.sigmoid(self.Linear(x))
+
+
 class ATTENTION(nn.Module):
     def __init__(self, config, hidden_size, mode='dot'):
         super(ATTENTION, self).__init__()

@@ -130,3 +130,32 @@ def test_premix_matches_reference_preprocessing(cuda):
     f_ref = np.stack([sr.features_ref(m, 256, 128)['mix_feas'] for m in ref.sum(1)])
     assert rel_err(batch['mix_feas'].cpu().numpy(), f_ref) < 1e-4
     assert tuple(batch['multi_spk_fea'].shape) == (B, S, 1 + L // 128, 129)
+
+
+def test_classifier_and_speaker_selection(cuda):
+    """n1: MIX_SPEECH_classifier (BLSTM 3x600 -> mean -> Linear -> sigmoid) against the oracle, then the
+    reference's eval flow: top_k_mask of its output -> speaker ids -> separation (EvalVer.py:424-470)."""
+    import copy
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    B, T = 3, 11
+    ref, ours = build_pair('lstm', 1, 129, T, False)
+    torch.manual_seed(7)
+    cls_ref = mr.MIX_SPEECH_classifier(ref['cfg'], 129, T, 101)
+    cls = d.MIX_SPEECH_classifier(129, T, 101).cuda()
+    assert list(cls.state_dict().keys()) == list(cls_ref.state_dict().keys())
+    cls.load_state_dict(copy.deepcopy(cls_ref.state_dict()))
+    feas = torch.rand(B, T, 129) * 2
+    with torch.no_grad():
+        p_ref = cls_ref(feas)
+        p = cls(feas.cuda())
+    assert tuple(p.shape) == (B, 101)
+    assert (p.cpu() - p_ref).abs().max().item() < 2e-5
+    # test-mode selection of the reference: alpha = -0.5, top_k = 2 -> exactly two speakers per utterance
+    mask = d.top_k_mask(p, -0.5, 2)
+    assert mask.is_cuda and torch.equal(mask.cpu(), mr.top_k_mask(p_ref, -0.5, 2))
+    idx = torch.nonzero(mask)[:, 1].view(B, 2)
+    with torch.no_grad():
+        r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, idx.cpu().numpy())
+    m = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj']).masks(feas.cuda(), idx)
+    assert (m.cpu() - r['masks']).abs().max().item() < 1e-4
