@@ -5,7 +5,7 @@
 // Frames are staged in shared memory so the 50-75 % frame overlap never re-reads HBM, two real
 // frames ride one complex transform (real/imag packing), and the 256-point transform runs on 16
 // lanes x 16 registers with one shared-memory transpose (fft256.cuh).
-#include "fft256.cuh"
+#include "fft256x2.cuh"
 
 namespace dl4ss {
 
@@ -18,7 +18,7 @@ constexpr int NBIN = 129;
 // loads with the others' FFTs, and the last wave is finer grained
 constexpr int K1_THREADS = 128;
 constexpr int K1_GROUPS = K1_THREADS / 16;
-constexpr int K1_FT = 2 * K1_GROUPS;
+constexpr int K1_FT = 4 * K1_GROUPS;         // four frames per group (two packed complex transforms)
 
 // exp(-2*pi*i*n1*k2/256) laid out [k2][n1] (fft256.cuh), built once per device
 __device__ float2 g_tw256[256];
@@ -38,140 +38,168 @@ static int ensure_twiddles(cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------ K1
-__device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT-class, max relative error 2^-23
+__device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT-class, max relative error 2^-23 (ftz: |X|^2 below 1.2e-38 reads as 0, far under eps)
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
-// FEAT / CPLX are compile time: the output loop is a third of the kernel's instructions
-template <typename WavT, int FEAT, bool CPLX>
+// FEAT / CPLX are compile time: the output loop is a third of the kernel's instructions.
+// A 16-lane group transforms FOUR consecutive frames: complex transform A carries frames (f0, f1) in its real /
+// imaginary parts, transform B frames (f2, f3), and the two transforms run packed on the FADD2/FMUL2/FFMA2 pipe
+// (fft256x2.cuh).  H128 (hop = n_fft/2, every reference config): the four frames span five half-frames, so a
+// lane loads 40 samples instead of 64.
+template <typename WavT>
+__device__ __forceinline__ float load_reflect(const WavT *__restrict__ w, int j, int L) {
+    j = (j < 0) ? -j : j;
+    j = (j >= L) ? 2 * (L - 1) - j : j;
+    return (float)w[j];
+}
+
+template <typename WavT, int FEAT, bool CPLX, bool H128>
 __global__ void __launch_bounds__(K1_THREADS)
 stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt,
-               const float *__restrict__ window, float eps, int conj,
+               const float *__restrict__ window, float eps, int conj, int pf_dist,
                float *__restrict__ feat, float2 *__restrict__ cplx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);                 // 256 float2
-    float2 *xch = tw + 256;                                            // groups * 272 float2
-    float *win = reinterpret_cast<float *>(xch + K1_GROUPS * DL4SS_XCH_FLOAT2);   // 256
+    float4 *xch = reinterpret_cast<float4 *>(smem_raw);                  // groups * 272 float4
+    float2 *tw = reinterpret_cast<float2 *>(xch + K1_GROUPS * DL4SS_XCH2_FLOAT4);     // 256 float2
+    float *win = reinterpret_cast<float *>(tw + 256);                    // 256
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x / tiles_per_utt;
     const int tile = blockIdx.x - b * tiles_per_utt;
     const int t0 = tile * K1_FT;
-    const int nf = min(K1_FT, T - t0);
 
+    // pull the waveform span of the CTA one resident wave ahead into L2 (no registers, no scoreboard): by the time
+    // that CTA runs, its loads are L2 hits instead of DRAM round trips
+    if (blockIdx.x + pf_dist < gridDim.x) {
+        const int pb = (blockIdx.x + pf_dist) / tiles_per_utt;
+        const int pt = (blockIdx.x + pf_dist) - pb * tiles_per_utt;
+        const int j = min(max(pt * K1_FT * hop - NFFT / 2 + tid * (int)(128 / sizeof(WavT)), 0), L - 1);
+        if (tid * (int)(128 / sizeof(WavT)) < (K1_FT - 1) * hop + NFFT) prefetch_l2(wav + (size_t)pb * L + j);
+    }
     for (int i = tid; i < NFFT; i += K1_THREADS) {
         tw[i] = g_tw256[i];
         win[i] = window[i];
     }
-
     __syncthreads();                       // twiddle / window tables: the kernel's only CTA-wide sync
 
     const int g = tid >> 4, l16 = tid & 15;
-    const int fa = 2 * g, fb = 2 * g + 1;
-    const bool va = fa < nf, vb = fb < nf;
+    const int f0 = t0 + 4 * g;
+    // frames past the end are clamped (valid loads, results never stored); no early exit: the two groups of a
+    // warp meet in __syncwarp / __shfl_sync
+    const int fr[4] = {min(f0, T - 1), min(f0 + 1, T - 1), min(f0 + 2, T - 1), min(f0 + 3, T - 1)};
+    const bool ok[4] = {f0 < T, f0 + 1 < T, f0 + 2 < T, f0 + 3 < T};
 
-    // Every 16-lane group pulls its two frames straight from global memory (64-byte coalesced rows per n2;
-    // frame t spans signal [t*hop-128, t*hop+128), reflect-padded at the utterance edges).  The 50-75 % overlap
-    // between neighbouring frames is served by L1/L2 (DRAM still sees each sample once), and without a
-    // staging phase the warps of a CTA never wait on each other.
-    float2 v[16];
+    // Every group pulls its frames straight from global memory (64-byte coalesced rows per n2; frame t spans signal
+    // [t*hop-128, t*hop+128), reflect-padded at the utterance edges).  The overlap between neighbouring groups is
+    // served by L1/L2 (DRAM sees each sample once); without a staging phase the warps never wait on each other.
+    cx2 v[16];
     {
         const WavT *w = wav + (size_t)b * L;
-        float xa[16], xb[16];
-        const int sa0 = (t0 + (va ? fa : 0)) * hop - NFFT / 2;
-        const int sb0 = (t0 + (vb ? fb : 0)) * hop - NFFT / 2;
-        if (sa0 >= 0 && sa0 + NFFT <= L) {
+        const int s0 = f0 * hop - NFFT / 2;
+        if (H128 && ok[3]) {
+            float h[5][8];
+            if (s0 >= 0 && s0 + 5 * (NFFT / 2) <= L) {
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) xa[n2] = (float)w[sa0 + l16 + 16 * n2];
-        } else {
+                for (int q = 0; q < 5; ++q)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) h[q][n] = (float)w[s0 + q * (NFFT / 2) + l16 + 16 * n];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) h[q][n] = load_reflect(w, s0 + q * (NFFT / 2) + l16 + 16 * n, L);
+            }
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
-                int j = sa0 + l16 + 16 * n2;
-                j = (j < 0) ? -j : j;
-                j = (j >= L) ? 2 * (L - 1) - j : j;
-                xa[n2] = (float)w[j];
+                const float2 wv = pbc(win[l16 + 16 * n2]);
+                const int q = n2 >> 3, n = n2 & 7;
+                v[n2].re = pmul(make_float2(h[q][n], h[q + 2][n]), wv);          // frames f0, f2
+                v[n2].im = pmul(make_float2(h[q + 1][n], h[q + 3][n]), wv);      // frames f1, f3
             }
-        }
-        if (sb0 >= 0 && sb0 + NFFT <= L) {
-#pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) xb[n2] = (float)w[sb0 + l16 + 16 * n2];
         } else {
+            const int sf[4] = {fr[0] * hop - NFFT / 2, fr[1] * hop - NFFT / 2, fr[2] * hop - NFFT / 2, fr[3] * hop - NFFT / 2};
+            const bool interior = (sf[0] >= 0) && (sf[3] + NFFT <= L);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
-                int j = sb0 + l16 + 16 * n2;
-                j = (j < 0) ? -j : j;
-                j = (j >= L) ? 2 * (L - 1) - j : j;
-                xb[n2] = (float)w[j];
-            }
-        }
+                float x[4];
+                if (interior) {
 #pragma unroll
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const float wv = win[l16 + 16 * n2];
-            v[n2] = make_float2(xa[n2] * wv, xb[n2] * wv);
+                    for (int i = 0; i < 4; ++i) x[i] = (float)w[sf[i] + l16 + 16 * n2];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = load_reflect(w, sf[i] + l16 + 16 * n2, L);
+                }
+                const float2 wv = pbc(win[l16 + 16 * n2]);
+                v[n2].re = pmul(make_float2(x[0], x[2]), wv);
+                v[n2].im = pmul(make_float2(x[1], x[3]), wv);
+            }
         }
     }
-    fft256_group<false>(v, l16, xch + g * DL4SS_XCH_FLOAT2, tw);
+    fft256x2_group<false>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
 
-    // split Z = FFT(xa + i*xb) into the two real-input spectra:
+    // split Z = FFT(xa + i*xb) into the two real-input spectra (per transform):
     //   XA[k] = (Z[k] + conj(Z[256-k]))/2 ,  XB[k] = (Z[k] - conj(Z[256-k]))/(2i)
     // lane holds Z[16*k1+l16] in v[k1]; Z[256-k] lives in lane (16-l16)&15, register 15-k1
     // (lane 0: own register (16-k1)&15).
-    const size_t rowa = ((size_t)b * T + t0 + fa) * NBIN + l16;
-    float *fpa = feat + rowa, *fpb = fpa + NBIN;
-    float2 *cpa = cplx + rowa, *cpb = cpa + NBIN;
+    size_t row[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[i] = ((size_t)b * T + fr[i]) * NBIN + l16;
     const int src = (16 - l16) & 15;
-    const float sgn = conj ? -1.0f : 1.0f;
+    const float sg = conj ? -0.5f : 0.5f;
+    const float2 half2 = pbc(0.5f), sgn2 = pbc(sg), nsgn2 = pbc(-sg);
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) {
-        float2 z = v[k1];
-        float px = __shfl_sync(0xffffffffu, v[15 - k1].x, src, 16);
-        float py = __shfl_sync(0xffffffffu, v[15 - k1].y, src, 16);
-        if (l16 == 0) {
-            px = v[(16 - k1) & 15].x;
-            py = v[(16 - k1) & 15].y;
-        }
-        float2 xa = make_float2(0.5f * (z.x + px), 0.5f * (z.y - py));
-        float2 xb = make_float2(0.5f * (z.y + py), -0.5f * (z.x - px));
+        const cx2 z = v[k1];
+        cx2 p;
+        p.re.x = __shfl_sync(0xffffffffu, v[15 - k1].re.x, src, 16);
+        p.re.y = __shfl_sync(0xffffffffu, v[15 - k1].re.y, src, 16);
+        p.im.x = __shfl_sync(0xffffffffu, v[15 - k1].im.x, src, 16);
+        p.im.y = __shfl_sync(0xffffffffu, v[15 - k1].im.y, src, 16);
+        if (l16 == 0) p = v[(16 - k1) & 15];
+        // 2*XA = (sre, dim) ; 2*XB = (sim, -dre)
+        const float2 sre = padd(z.re, p.re), dim = psub(z.im, p.im), sim = padd(z.im, p.im), dre = psub(z.re, p.re);
         if (FEAT != DL4SS_FEAT_NONE) {
-            float ma = sqrt_approx(fmaf(xa.x, xa.x, xa.y * xa.y));
-            float mb = sqrt_approx(fmaf(xb.x, xb.x, xb.y * xb.y));
-            if (FEAT == DL4SS_FEAT_LOG) {
-                ma = logf(ma + eps);
-                mb = logf(mb + eps);
+            const float2 qa = pfma(sre, sre, pmul(dim, dim)), qb = pfma(sim, sim, pmul(dre, dre));
+            float m[4] = {0.5f * sqrt_approx(qa.x), 0.5f * sqrt_approx(qb.x), 0.5f * sqrt_approx(qa.y), 0.5f * sqrt_approx(qb.y)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (FEAT == DL4SS_FEAT_LOG) m[i] = logf(m[i] + eps);
+                if (ok[i]) feat[row[i] + 16 * k1] = m[i];
             }
-            if (va) fpa[16 * k1] = ma;
-            if (vb) fpb[16 * k1] = mb;
         }
         if (CPLX) {
-            if (va) cpa[16 * k1] = make_float2(xa.x, sgn * xa.y);
-            if (vb) cpb[16 * k1] = make_float2(xb.x, sgn * xb.y);
+            const float2 are = pmul(sre, half2), aim = pmul(dim, sgn2), bre = pmul(sim, half2), bim = pmul(dre, nsgn2);
+            if (ok[0]) cplx[row[0] + 16 * k1] = make_float2(are.x, aim.x);
+            if (ok[1]) cplx[row[1] + 16 * k1] = make_float2(bre.x, bim.x);
+            if (ok[2]) cplx[row[2] + 16 * k1] = make_float2(are.y, aim.y);
+            if (ok[3]) cplx[row[3] + 16 * k1] = make_float2(bre.y, bim.y);
         }
     }
     if (l16 == 0) {   // Nyquist bin: Z[128] = XA[128] + i*XB[128], both real
-        float xa = v[8].x, xb = v[8].y;
-        if (FEAT != DL4SS_FEAT_NONE) {
-            float ma = fabsf(xa), mb = fabsf(xb);
-            if (FEAT == DL4SS_FEAT_LOG) {
-                ma = logf(ma + eps);
-                mb = logf(mb + eps);
+        const float x[4] = {v[8].re.x, v[8].im.x, v[8].re.y, v[8].im.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!ok[i]) continue;
+            if (FEAT != DL4SS_FEAT_NONE) {
+                float m = fabsf(x[i]);
+                if (FEAT == DL4SS_FEAT_LOG) m = logf(m + eps);
+                feat[row[i] + 128] = m;
             }
-            if (va) fpa[128] = ma;
-            if (vb) fpb[128] = mb;
-        }
-        if (CPLX) {
-            if (va) cpa[128] = make_float2(xa, 0.0f);
-            if (vb) cpb[128] = make_float2(xb, 0.0f);
+            if (CPLX) cplx[row[i] + 128] = make_float2(x[i], 0.0f);
         }
     }
 }
 
 // Masked spectra of two (source, frame) items -> one complex inverse transform: on return v[n1].x / .y hold the
-// (unnormalised, unwindowed) time samples 16*n1 + l16 of item a / item b.
+// (unnormalised, unwindowed) time samples 16*n1 + l16 of item a / item b.  Items flagged invalid still carry
+// in-range (clamped) indices: they are loaded like any other and their samples are never stored, which keeps
+// the address arithmetic out of predicated code.
 template <int MASK_KIND>
 __device__ __forceinline__ void masked_pair_ifft(const float *__restrict__ mask, const float2 *__restrict__ spec,
-                                                 int b, int S, int T, int sa, int ta, bool va, int sb, int tb, bool vb,
+                                                 int b, int S, int T, int sa, int ta, int sb, int tb,
                                                  int l16, float2 *xch_g, const float2 *tw, float2 (&v)[16]) {
     const int src = (16 - l16) & 15;
     float2 pa[8], pb[8], pa_n = make_float2(0.f, 0.f), pb_n = make_float2(0.f, 0.f);
@@ -180,12 +208,12 @@ __device__ __forceinline__ void masked_pair_ifft(const float *__restrict__ mask,
         const float2 *rb = spec + (((size_t)b * S + sb) * T + tb) * NBIN;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            pa[m] = va ? ra[16 * m + l16] : make_float2(0.f, 0.f);
-            pb[m] = vb ? rb[16 * m + l16] : make_float2(0.f, 0.f);
+            pa[m] = ra[16 * m + l16];
+            pb[m] = rb[16 * m + l16];
         }
         if (l16 == 0) {
-            if (va) pa_n = ra[128];
-            if (vb) pb_n = rb[128];
+            pa_n = ra[128];
+            pb_n = rb[128];
         }
     } else {
         const float2 *xa = spec + ((size_t)b * T + ta) * NBIN;
@@ -195,35 +223,35 @@ __device__ __forceinline__ void masked_pair_ifft(const float *__restrict__ mask,
         float2 xva[8], xvb[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            xva[m] = va ? xa[16 * m + l16] : make_float2(0.f, 0.f);
-            xvb[m] = vb ? xb[16 * m + l16] : make_float2(0.f, 0.f);
+            xva[m] = xa[16 * m + l16];
+            xvb[m] = xb[16 * m + l16];
         }
         if (MASK_KIND == DL4SS_MASK_REAL) {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                float ka = va ? mask[ma + 16 * m + l16] : 0.f;
-                float kb = vb ? mask[mb + 16 * m + l16] : 0.f;
+                float ka = mask[ma + 16 * m + l16];
+                float kb = mask[mb + 16 * m + l16];
                 pa[m] = make_float2(ka * xva[m].x, ka * xva[m].y);
                 pb[m] = make_float2(kb * xvb[m].x, kb * xvb[m].y);
             }
             if (l16 == 0) {
-                if (va) { float k = mask[ma + 128]; float2 x = xa[128]; pa_n = make_float2(k * x.x, k * x.y); }
-                if (vb) { float k = mask[mb + 128]; float2 x = xb[128]; pb_n = make_float2(k * x.x, k * x.y); }
+                { float k = mask[ma + 128]; float2 x = xa[128]; pa_n = make_float2(k * x.x, k * x.y); }
+                { float k = mask[mb + 128]; float2 x = xb[128]; pb_n = make_float2(k * x.x, k * x.y); }
             }
         } else {
             const float2 *cma = reinterpret_cast<const float2 *>(mask) + ma;
             const float2 *cmb = reinterpret_cast<const float2 *>(mask) + mb;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                float2 ka = va ? cma[16 * m + l16] : make_float2(0.f, 0.f);
-                float2 kb = vb ? cmb[16 * m + l16] : make_float2(0.f, 0.f);
+                float2 ka = cma[16 * m + l16];
+                float2 kb = cmb[16 * m + l16];
                 // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
                 pa[m] = make_float2(ka.x * xva[m].x - ka.y * xva[m].y, ka.x * xva[m].y + ka.y * xva[m].x);
                 pb[m] = make_float2(kb.x * xvb[m].x - kb.y * xvb[m].y, kb.x * xvb[m].y + kb.y * xvb[m].x);
             }
             if (l16 == 0) {
-                if (va) { float2 k = cma[128]; float2 x = xa[128]; pa_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
-                if (vb) { float2 k = cmb[128]; float2 x = xb[128]; pb_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+                { float2 k = cma[128]; float2 x = xa[128]; pa_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
+                { float2 k = cmb[128]; float2 x = xb[128]; pb_n = make_float2(k.x * x.x - k.y * x.y, 0.f); }
             }
         }
     }
@@ -302,7 +330,7 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
         const int tb = t_lo + (vb ? ib / S : 0), sb = vb ? ib % S : 0;
 
         float2 v[16];
-        masked_pair_ifft<MASK_KIND>(mask, spec, b, S, T, sa, ta, va, sb, tb, vb, l16, xch + g * DL4SS_XCH_FLOAT2, tw, v);
+        masked_pair_ifft<MASK_KIND>(mask, spec, b, S, T, sa, ta, sb, tb, l16, xch + g * DL4SS_XCH_FLOAT2, tw, v);
         float *ya = ybuf + (size_t)ia * NFFT;
         float *yb = ybuf + (size_t)ib * NFFT;
 #pragma unroll
@@ -404,79 +432,204 @@ istft256_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec,
 
 // ------------------------------------------------------------------------------------ K6, hop = n_fft/2
 // Every reference config has hop 128 = half a frame: exactly two frames cover each output sample.  A 16-lane
-// group transforms the frame pair (2q, 2q+1) of ONE source, so the hop block between them is summed, normalised
-// and stored straight from registers; the block after frame 2q+1 needs the lower half of the NEXT pair's first
-// frame, which every group parks in an 8 KB exchange buffer (one __syncthreads).  No frame buffer, no separate
-// overlap-add pass; the group after the tile's last pair is recomputed as halo by the neighbouring CTA.
+// group inverse-transforms the frame pair (2q, 2q+1) of TWO sources at once (the two packed transforms of
+// fft256x2.cuh; the mixture spectrum is loaded once for both), so the hop block between the two frames is summed,
+// normalised and stored straight from registers; the block after frame 2q+1 needs the lower half of the NEXT
+// pair's first frame, which every group parks in a 16 KB exchange buffer (one __syncthreads).  No frame buffer, no
+// separate overlap-add pass; the pair after the tile's last one is recomputed as halo by the neighbouring CTA.
 constexpr int K6H_PAIRS = STFT_GROUPS - 1;       // pairs a CTA owns (the 16th group is the halo pair)
 
 template <int MASK_KIND>
-__global__ void __launch_bounds__(STFT_THREADS)
+__global__ void __launch_bounds__(STFT_THREADS, 2)
 istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec, int S, int T, int tiles_per_src,
-                  const float *__restrict__ window, float *__restrict__ out) {
+                  int pf_dist, const float *__restrict__ window, float *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *xch = tw + 256;
-    float *win = reinterpret_cast<float *>(xch + STFT_GROUPS * DL4SS_XCH_FLOAT2);   // 256: window / N
-    float *inv = win + NFFT;                                                        // 128: 1 / (w^2[j] + w^2[j+128])
-    float *exch = inv + NFFT / 2;                                                   // [groups][128]
+    float4 *xch = reinterpret_cast<float4 *>(smem_raw);                              // groups * 272
+    float2 *tw = reinterpret_cast<float2 *>(xch + STFT_GROUPS * DL4SS_XCH2_FLOAT4);  // 256
+    float2 *exch = tw + 256;                                                         // [groups][128] (src0, src1)
+    float *wlo = reinterpret_cast<float *>(exch + STFT_GROUPS * (NFFT / 2));         // 128: w[j] / (N * env[j])
+    float *whi = wlo + NFFT / 2;                                                     // 128: w[j+128] / (N * env[j])
 
     const int tid = threadIdx.x;
+    const int SP = (S + 1) >> 1;
     int bid = blockIdx.x;
-    const int s = bid % S; bid /= S;                 // sources of an utterance run back to back: X stays in L2
+    const int sp = bid % SP; bid /= SP;              // source pairs of an utterance run back to back: X stays in L2
     const int tile = bid % tiles_per_src;
     const int b = bid / tiles_per_src;
+    const int s0 = 2 * sp, s1 = min(s0 + 1, S - 1);
+    const bool two = (s0 + 1 < S);
     const int Lout = (NFFT / 2) * (T - 1);
 
-    tw[tid] = g_tw256[tid];
-    {
-        const float wt = window[tid];
-        win[tid] = wt * (1.0f / NFFT);
-        if (tid < NFFT / 2) {
-            const float w2 = window[tid + NFFT / 2];
-            const float e = wt * wt + w2 * w2;
-            inv[tid] = (e > 1.17549435e-38f) ? 1.0f / e : 1.0f;
+    const int g = tid >> 4, l16 = tid & 15;
+    // pull the rows of the CTA one resident wave ahead into L2 (no registers, no scoreboard)
+    if (blockIdx.x + pf_dist < gridDim.x) {
+        int pid = blockIdx.x + pf_dist;
+        const int psp = pid % SP; pid /= SP;
+        const int ptile = pid % tiles_per_src, pb = pid / tiles_per_src;
+        const int pta = min(2 * (ptile * K6H_PAIRS + g), T - 1);
+        const int rows = min(2, T - pta);            // frames 2q, 2q+1 are adjacent rows
+        const char *px = reinterpret_cast<const char *>(spec + (MASK_KIND == DL4SS_MASK_NONE
+                             ? (((size_t)pb * S + 2 * psp) * T + pta) * NBIN : ((size_t)pb * T + pta) * NBIN));
+        const int xbytes = rows * NBIN * 8;
+        if (l16 * 128 < xbytes) prefetch_l2(px + l16 * 128);
+        if (l16 == 0 && 16 * 128 < xbytes) prefetch_l2(px + 16 * 128);
+        if (MASK_KIND != DL4SS_MASK_NONE) {
+            const int mb = (MASK_KIND == DL4SS_MASK_COMPLEX) ? 8 : 4, mbytes = rows * NBIN * mb;
+            for (int sidx = 2 * psp; sidx < min(2 * psp + 2, S); ++sidx) {
+                const char *pm = reinterpret_cast<const char *>(mask) + (((size_t)pb * S + sidx) * T + pta) * NBIN * mb;
+                if (l16 * 128 < mbytes) prefetch_l2(pm + l16 * 128);
+                if (l16 == 0 && 16 * 128 < mbytes) prefetch_l2(pm + 16 * 128);
+            }
+        } else if (2 * psp + 1 < S) {
+            const char *p1 = px + (size_t)T * NBIN * 8;
+            if (l16 * 128 < xbytes) prefetch_l2(p1 + l16 * 128);
+            if (l16 == 0 && 16 * 128 < xbytes) prefetch_l2(p1 + 16 * 128);
         }
+    }
+    tw[tid] = g_tw256[tid];
+    if (tid < NFFT / 2) {
+        // out[j] = (frame_hi[j+128]*w[j+128] + frame_lo[j]*w[j]) / (w[j]^2 + w[j+128]^2), 1/N of the inverse folded in
+        const float w1 = window[tid], w2 = window[tid + NFFT / 2];
+        const float e = w1 * w1 + w2 * w2;
+        const float inv = ((e > 1.17549435e-38f) ? 1.0f / e : 1.0f) * (1.0f / NFFT);
+        wlo[tid] = w1 * inv;
+        whi[tid] = w2 * inv;
     }
     __syncthreads();
 
-    const int g = tid >> 4, l16 = tid & 15;
     const int q = tile * K6H_PAIRS + g;              // group K6H_PAIRS is the halo pair
     const int ta = 2 * q, tb = 2 * q + 1;
-    const bool va = ta < T, vb = (tb < T) && (g < K6H_PAIRS);     // the halo group only needs its first frame
+    // out-of-range frames are clamped: loaded like any other, never stored
+    const int tac = min(ta, T - 1);
+    const int tbc = (tb < T && g < K6H_PAIRS) ? tb : tac;     // the halo group only needs its first frame
 
-    float2 v[16];
-    masked_pair_ifft<MASK_KIND>(mask, spec, b, S, T, s, va ? ta : 0, va, s, vb ? tb : 0, vb, l16,
-                                xch + g * DL4SS_XCH_FLOAT2, tw, v);
+    cx2 v[16];
+    {
+        // pa / pb: masked spectra of frame a / b, packed over the two sources
+        cx2 pa[8], pb[8];
+        float2 pa_n, pb_n;                           // Nyquist bin (real part only), lane 0
+        if (MASK_KIND == DL4SS_MASK_NONE) {
+            const float2 *ra0 = spec + (((size_t)b * S + s0) * T + tac) * NBIN, *ra1 = spec + (((size_t)b * S + s1) * T + tac) * NBIN;
+            const float2 *rb0 = spec + (((size_t)b * S + s0) * T + tbc) * NBIN, *rb1 = spec + (((size_t)b * S + s1) * T + tbc) * NBIN;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2 a0 = ra0[16 * m + l16], a1 = ra1[16 * m + l16], b0 = rb0[16 * m + l16], b1 = rb1[16 * m + l16];
+                pa[m] = cx2{make_float2(a0.x, a1.x), make_float2(a0.y, a1.y)};
+                pb[m] = cx2{make_float2(b0.x, b1.x), make_float2(b0.y, b1.y)};
+            }
+            pa_n = pb_n = make_float2(0.f, 0.f);
+            if (l16 == 0) {
+                pa_n = make_float2(ra0[128].x, ra1[128].x);
+                pb_n = make_float2(rb0[128].x, rb1[128].x);
+            }
+        } else {
+            const float2 *xa = spec + ((size_t)b * T + tac) * NBIN;
+            const float2 *xb = spec + ((size_t)b * T + tbc) * NBIN;
+            const size_t ma0 = (((size_t)b * S + s0) * T + tac) * NBIN, ma1 = (((size_t)b * S + s1) * T + tac) * NBIN;
+            const size_t mb0 = (((size_t)b * S + s0) * T + tbc) * NBIN, mb1 = (((size_t)b * S + s1) * T + tbc) * NBIN;
+            float2 xva[8], xvb[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                xva[m] = xa[16 * m + l16];
+                xvb[m] = xb[16 * m + l16];
+            }
+            if (MASK_KIND == DL4SS_MASK_REAL) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float2 ka = make_float2(mask[ma0 + 16 * m + l16], mask[ma1 + 16 * m + l16]);
+                    const float2 kb = make_float2(mask[mb0 + 16 * m + l16], mask[mb1 + 16 * m + l16]);
+                    pa[m] = cx2{pmul(ka, pbc(xva[m].x)), pmul(ka, pbc(xva[m].y))};
+                    pb[m] = cx2{pmul(kb, pbc(xvb[m].x)), pmul(kb, pbc(xvb[m].y))};
+                }
+                pa_n = pb_n = make_float2(0.f, 0.f);
+                if (l16 == 0) {
+                    const float xan = xa[128].x, xbn = xb[128].x;
+                    pa_n = make_float2(mask[ma0 + 128] * xan, mask[ma1 + 128] * xan);
+                    pb_n = make_float2(mask[mb0 + 128] * xbn, mask[mb1 + 128] * xbn);
+                }
+            } else {
+                const float2 *cm = reinterpret_cast<const float2 *>(mask);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float2 a0 = cm[ma0 + 16 * m + l16], a1 = cm[ma1 + 16 * m + l16];
+                    const float2 b0 = cm[mb0 + 16 * m + l16], b1 = cm[mb1 + 16 * m + l16];
+                    const float2 kar = make_float2(a0.x, a1.x), kai = make_float2(a0.y, a1.y);
+                    const float2 kbr = make_float2(b0.x, b1.x), kbi = make_float2(b0.y, b1.y);
+                    // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
+                    pa[m] = cx2{pfnma(kai, pbc(xva[m].y), pmul(kar, pbc(xva[m].x))), pfma(kai, pbc(xva[m].x), pmul(kar, pbc(xva[m].y)))};
+                    pb[m] = cx2{pfnma(kbi, pbc(xvb[m].y), pmul(kbr, pbc(xvb[m].x))), pfma(kbi, pbc(xvb[m].x), pmul(kbr, pbc(xvb[m].y)))};
+                }
+                pa_n = pb_n = make_float2(0.f, 0.f);
+                if (l16 == 0) {
+                    const float2 xan = xa[128], xbn = xb[128];
+                    const float2 a0 = cm[ma0 + 128], a1 = cm[ma1 + 128], b0 = cm[mb0 + 128], b1 = cm[mb1 + 128];
+                    pa_n = make_float2(a0.x * xan.x - a0.y * xan.y, a1.x * xan.x - a1.y * xan.y);
+                    pb_n = make_float2(b0.x * xbn.x - b0.y * xbn.y, b1.x * xbn.x - b1.y * xbn.y);
+                }
+            }
+        }
+        if (l16 == 0) {   // DC bin: irfft ignores the imaginary part
+            pa[0].im = make_float2(0.f, 0.f);
+            pb[0].im = make_float2(0.f, 0.f);
+        }
+        // Z[k] = A[k] + i*B[k] for k <= 128 ; Z[256-k] = conj(A[k]) + i*conj(B[k])
+        const int src = (16 - l16) & 15;
+        cx2 c[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            v[m] = cx2{psub(pa[m].re, pb[m].im), padd(pa[m].im, pb[m].re)};
+            c[m] = cx2{padd(pa[m].re, pb[m].im), psub(pb[m].re, pa[m].im)};
+        }
+#pragma unroll
+        for (int m = 8; m < 16; ++m) {
+            cx2 t;
+            t.re.x = __shfl_sync(0xffffffffu, c[15 - m].re.x, src, 16);
+            t.re.y = __shfl_sync(0xffffffffu, c[15 - m].re.y, src, 16);
+            t.im.x = __shfl_sync(0xffffffffu, c[15 - m].im.x, src, 16);
+            t.im.y = __shfl_sync(0xffffffffu, c[15 - m].im.y, src, 16);
+            if (l16 == 0) {
+                if (m == 8) t = cx2{pa_n, pb_n};
+                else t = c[16 - m];
+            }
+            v[m] = t;
+        }
+    }
+    fft256x2_group<true>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
+    // v[n1].re = samples 16*n1+l16 of frame a (src0, src1) ; v[n1].im = frame b
 
-    // park the windowed lower half of the first frame for the previous group
-    float *ex = exch + g * (NFFT / 2);
+    // park the windowed, normalised lower half of the first frame for the previous group
+    float2 *ex = exch + g * (NFFT / 2);
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
         const int j = 16 * n1 + l16;
-        ex[j] = v[n1].x * win[j];
+        ex[j] = pmul(v[n1].re, pbc(wlo[j]));
     }
     __syncthreads();
     if (g >= K6H_PAIRS) return;
 
-    float *o = out + ((size_t)b * S + s) * Lout;
+    float *o0 = out + ((size_t)b * S + s0) * Lout + l16;
+    float *o1 = out + ((size_t)b * S + s1) * Lout + l16;
     // block 2q: frame 2q upper half + frame 2q+1 lower half (both in registers)
     if (tb <= T - 1) {
-        float *ob = o + (size_t)ta * (NFFT / 2) + l16;
+        const size_t off = (size_t)ta * (NFFT / 2);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
             const int j = 16 * n1 + l16;
-            ob[16 * n1] = (v[n1 + 8].x * win[j + NFFT / 2] + v[n1].y * win[j]) * inv[j];
+            const float2 r = pfma(v[n1 + 8].re, pbc(whi[j]), pmul(v[n1].im, pbc(wlo[j])));
+            o0[off + 16 * n1] = r.x;
+            if (two) o1[off + 16 * n1] = r.y;
         }
     }
     // block 2q+1: frame 2q+1 upper half + the next pair's first frame lower half
     if (tb + 1 <= T - 1) {
-        const float *nx = exch + (g + 1) * (NFFT / 2);
-        float *ob = o + (size_t)tb * (NFFT / 2) + l16;
+        const float2 *nx = exch + (g + 1) * (NFFT / 2);
+        const size_t off = (size_t)tb * (NFFT / 2);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
             const int j = 16 * n1 + l16;
-            ob[16 * n1] = (v[n1 + 8].y * win[j + NFFT / 2] + nx[j]) * inv[j];
+            const float2 r = pfma(v[n1 + 8].im, pbc(whi[j]), nx[j]);
+            o0[off + 16 * n1] = r.x;
+            if (two) o1[off + 16 * n1] = r.y;
         }
     }
 }
@@ -503,17 +656,24 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
     if (B == 0) return DL4SS_OK;
     const int T = 1 + L / hop;
     const int tiles = cdiv(T, K1_FT);
-    const size_t smem = 256 * sizeof(float2) + K1_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                        NFFT * sizeof(float);
+    const size_t smem = K1_GROUPS * DL4SS_XCH2_FLOAT4 * sizeof(float4) + 256 * sizeof(float2) + NFFT * sizeof(float);
+    const int pf_dist = 4 * sm_count();          // CTAs resident at once (4 per SM: registers / shared memory)
+    const bool h128 = (hop == NFFT / 2);
     cudaStream_t st = (cudaStream_t)stream;
     { int rc = ensure_twiddles(st); if (rc) return rc; }
     const long long grid = (long long)B * tiles;
     DL4SS_CHECK_ARG(grid < (1ll << 31), "stft_feat: grid too large");
 #define LAUNCH_K1(WT, FM, CP)                                                                                  \
     do {                                                                                                        \
-        DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        stft256_kernel<WT, FM, CP><<<(unsigned)grid, K1_THREADS, smem, st>>>(                                   \
-            (const WT *)wav, L, hop, T, tiles, window, eps, conj, feat_out, (float2 *)cplx_out);                \
+        if (h128) {                                                                                             \
+            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            stft256_kernel<WT, FM, CP, true><<<(unsigned)grid, K1_THREADS, smem, st>>>(                         \
+                (const WT *)wav, L, hop, T, tiles, window, eps, conj, pf_dist, feat_out, (float2 *)cplx_out);            \
+        } else {                                                                                                \
+            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            stft256_kernel<WT, FM, CP, false><<<(unsigned)grid, K1_THREADS, smem, st>>>(                        \
+                (const WT *)wav, L, hop, T, tiles, window, eps, conj, pf_dist, feat_out, (float2 *)cplx_out);            \
+        }                                                                                                       \
     } while (0)
 #define DISPATCH_K1(WT)                                                                                         \
     do {                                                                                                        \
@@ -553,15 +713,16 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
         { int rc = ensure_twiddles(st0); if (rc) return rc; }
         const int pairs = (T + 1) / 2;
         const int tiles_h = cdiv(pairs, K6H_PAIRS);
-        const size_t smem_h = 256 * sizeof(float2) + STFT_GROUPS * DL4SS_XCH_FLOAT2 * sizeof(float2) +
-                              (NFFT + NFFT / 2) * sizeof(float) + (size_t)STFT_GROUPS * (NFFT / 2) * sizeof(float);
-        const long long grid_h = (long long)B * S * tiles_h;
+        const size_t smem_h = STFT_GROUPS * DL4SS_XCH2_FLOAT4 * sizeof(float4) + 256 * sizeof(float2) +
+                              (size_t)STFT_GROUPS * (NFFT / 2) * sizeof(float2) + NFFT * sizeof(float);
+        const int pf_dist = 2 * sm_count();      // CTAs resident at once (2 per SM: 128 registers x 256 threads)
+        const long long grid_h = (long long)B * ((S + 1) / 2) * tiles_h;
         DL4SS_CHECK_ARG(grid_h < (1ll << 31), "mask_istft: grid too large");
 #define LAUNCH_H128(KIND)                                                                                       \
         do {                                                                                                    \
             DL4SS_CUDA(cudaFuncSetAttribute(istft_h128_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h)); \
             istft_h128_kernel<KIND><<<(unsigned)grid_h, STFT_THREADS, smem_h, st0>>>(                           \
-                mask, (const float2 *)spec, S, T, tiles_h, window, wav_out);                                    \
+                mask, (const float2 *)spec, S, T, tiles_h, pf_dist, window, wav_out);                                    \
         } while (0)
         if (mask_kind == DL4SS_MASK_NONE) LAUNCH_H128(DL4SS_MASK_NONE);
         else if (mask_kind == DL4SS_MASK_REAL) LAUNCH_H128(DL4SS_MASK_REAL);
