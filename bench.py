@@ -71,11 +71,14 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi in loop mode.  Called BEFORE the warm-up steps: its start-up (NVML init) can stall the
+        driver for milliseconds, which must not land inside the timed region."""
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '250'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -84,12 +87,25 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.01)
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.08)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -97,7 +113,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        rows = self.rows
+        if self.t0 is not None:      # samples taken while the timed region ran (the one just after it if it was short)
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t1 + 0.06]
+            rows = inside or rows[-1:]
+        for _, r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 6:
                 continue
@@ -368,20 +388,24 @@ def run_train(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 1)):
-        one_step()
-    barrier()
-    n0 = d.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        one_step()
+    if rank == 0:
+        sampler.wait_first()
     barrier()
+    n0 = d.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         loss = one_step()[0]
     e1.record()
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     launches = d.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
@@ -412,7 +436,8 @@ def workload_config(B):
             'n_fft': W['n_fft'], 'hop': W['hop'], 'speakers': W['S'],
             'encoder': '%s %dx%d bidirectional' % (W['cell'].upper(), W['layers'], W['H']),
             'embedding': W['E'], 'attention': 'dot + ADDJUST self-tune', 'mask': 'real sigmoid',
-            'l2': 'working set >> 126 MB L2 (xproj 769 MB/layer at B=256) and 4 rotating input batches'}
+            'l2': 'working set >> 126 MB L2 (xproj 769 MB/layer at B=256) and 4 rotating input batches',
+            'launch': 'one CUDA graph per step (GraphedSeparator); the rotating batch is copied device-to-device into its static input inside the timed region'}
 
 
 def main():
@@ -425,6 +450,7 @@ def main():
     ap.add_argument('--ref-utts', type=int, default=16, help='utterances per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-utts', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', type=int, default=1, help='1: replay the step from one CUDA graph (default); 0: eager launches')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="'train': BASELINE configs[3], STFT -> encoder -> masks -> loss -> backward -> all-reduce -> Adam")
     ap.add_argument('--train-batch', type=int, default=64, help='utterances per GPU per training step')
@@ -461,23 +487,33 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value")
-    for i in range(args.warmup):
-        sep.separate(wavs[i % len(wavs)], idx, check_index=False)
-    barrier()
+    # ---- device-resident throughput ("value"): the step is one CUDA graph (GraphedSeparator), replayed per batch;
+    # the rotating input batch is copied device-to-device into the graph's static input inside the timed region
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
         sampler.start()
+    sep.separate(wavs[0], idx, check_index=False)      # first use: weight planes, packed W_hh, twiddles
     n0 = d.launch_count()
+    sep.separate(wavs[1 % len(wavs)], idx, check_index=False)
+    launches_per_step = d.launch_count() - n0          # kernels of ours in one step (the graph replays exactly these)
+    step_fn = d.GraphedSeparator(sep, B, W['L'], W['S'], device=device) if args.graph else \
+        (lambda w, i: sep.separate(w, i, check_index=False))
+    for i in range(args.warmup):
+        step_fn(wavs[i % len(wavs)], idx)
+    if rank == 0:
+        sampler.wait_first()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for i in range(args.steps):
-        out = sep.separate(wavs[i % len(wavs)], idx, check_index=False)
+        out = step_fn(wavs[i % len(wavs)], idx)
     e1.record()
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
-    launches = d.launch_count() - n0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public call with HOST buffers ("e2e"): pinned waveforms in, pinned separated
@@ -486,7 +522,7 @@ def main():
     h_idx = idx.cpu().pin_memory()
     Lout = W['hop'] * (W['L'] // W['hop'])
     h_outs = [torch.empty(B, W['S'], Lout, dtype=torch.float32).pin_memory() for _ in range(3)]
-    pipe = d.HostPipeline(sep, B, W['L'], W['S'], depth=2, device=device)
+    pipe = d.HostPipeline(sep, B, W['L'], W['S'], depth=2, device=device, graphs=bool(args.graph))
     for i in range(max(8, args.warmup)):      # also lets the PCIe link leave its idle (down-trained) state
         pipe.submit(h_in[i % 4], h_idx, h_outs[i % 3])
     pipe.drain()

@@ -503,8 +503,11 @@ istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spe
     const int tac = min(ta, T - 1);
     const int tbc = (tb < T && g < K6H_PAIRS) ? tb : tac;     // the halo group only needs its first frame
 
+    // warps whose two groups both lie past the last frame (last tile of a source) skip the transform; the test is
+    // warp-uniform because the groups meet in __syncwarp / __shfl_sync
+    const bool warp_live = 2 * (tile * K6H_PAIRS + (g & ~1)) < T;
     cx2 v[16];
-    {
+    if (warp_live) {
         // pa / pb: masked spectra of frame a / b, packed over the two sources
         cx2 pa[8], pb[8];
         float2 pa_n, pb_n;                           // Nyquist bin (real part only), lane 0
@@ -536,8 +539,8 @@ istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spe
             if (MASK_KIND == DL4SS_MASK_REAL) {
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
-                    const float2 ka = make_float2(mask[ma0 + 16 * m + l16], mask[ma1 + 16 * m + l16]);
-                    const float2 kb = make_float2(mask[mb0 + 16 * m + l16], mask[mb1 + 16 * m + l16]);
+                    const float2 ka = make_float2(__ldcs(mask + ma0 + 16 * m + l16), __ldcs(mask + ma1 + 16 * m + l16));
+                    const float2 kb = make_float2(__ldcs(mask + mb0 + 16 * m + l16), __ldcs(mask + mb1 + 16 * m + l16));
                     pa[m] = cx2{pmul(ka, pbc(xva[m].x)), pmul(ka, pbc(xva[m].y))};
                     pb[m] = cx2{pmul(kb, pbc(xvb[m].x)), pmul(kb, pbc(xvb[m].y))};
                 }
@@ -593,18 +596,24 @@ istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spe
             }
             v[m] = t;
         }
-    }
-    fft256x2_group<true>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
-    // v[n1].re = samples 16*n1+l16 of frame a (src0, src1) ; v[n1].im = frame b
+        fft256x2_group<true>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
+        // v[n1].re = samples 16*n1+l16 of frame a (src0, src1) ; v[n1].im = frame b
 
-    // park the windowed, normalised lower half of the first frame for the previous group
-    float2 *ex = exch + g * (NFFT / 2);
+        // park the windowed, normalised lower half of the first frame for the previous group
+        float2 *ex = exch + g * (NFFT / 2);
 #pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) {
-        const int j = 16 * n1 + l16;
-        ex[j] = pmul(v[n1].re, pbc(wlo[j]));
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const int j = 16 * n1 + l16;
+            ex[j] = pmul(v[n1].re, pbc(wlo[j]));
+        }
     }
-    __syncthreads();
+    // The parked half frame is consumed by the group before: inside a warp that is a __syncwarp, across warps only
+    // warp w-1 waits for warp w (named barrier 1+w, 64 threads: 32 arrive, 32 sync) - no CTA-wide barrier, so a
+    // warp whose loads landed late holds back one neighbour instead of all eight.
+    const int warp = tid >> 5;
+    __syncwarp();
+    if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp + 1) : "memory");
+    if (warp < STFT_THREADS / 32 - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 2) : "memory");
     if (g >= K6H_PAIRS) return;
 
     float *o0 = out + ((size_t)b * S + s0) * Lout + l16;

@@ -56,6 +56,7 @@ class Separator(object):
         E = lin.out_features // F
         out = M.emb_attn_mask(hidden, lin.weight, lin.bias, q, F, E,
                               complex_mask=self.complex_mask, decompress=True, h_planes=extras.get('planes'))
+        self.last_err = err          # device flag of the embedding gather (GraphedSeparator.check_index reads it)
         if check_index and int(err.item()):
             raise IndexError('index out of range in self')
         return out
@@ -75,6 +76,49 @@ class Separator(object):
     __call__ = separate
 
 
+class GraphedSeparator(object):
+    """The whole waveform -> separated-waveforms step of a `Separator` for one fixed (B, L, S), captured ONCE in a
+    CUDA graph: the ~130 kernel launches of a step become a single cudaGraphLaunch, so the GPU never waits for
+    the host (python + ctypes per launch) and host scheduling jitter cannot stretch a step.
+
+        gs = GraphedSeparator(sep, B, L, S)
+        out = gs(wav, idx)          # copies into the static inputs, replays, returns the static output `gs.out`
+    `gs.wav` / `gs.idx` / `gs.out` are static device tensors: fill the inputs in place and call `gs.replay()` to
+    skip the device-to-device copies; consume `gs.out` before the next replay.  Speaker indices are not range
+    checked inside the graph; `gs.check_index()` reads the gather kernel's error flag of the last replay."""
+
+    def __init__(self, separator, B, L, S, wav_dtype=torch.float32, device=None):
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.sep = separator
+        self.wav = torch.zeros(B, L, device=dev, dtype=wav_dtype)
+        self.idx = torch.zeros(B, S, device=dev, dtype=torch.int64)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):          # first-use work (weight planes, twiddles, workspaces) stays outside the graph
+            separator.separate(self.wav, self.idx, check_index=False)
+            separator.separate(self.wav, self.idx, check_index=False)
+        side.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.out = separator.separate(self.wav, self.idx, check_index=False)
+            self.err = separator.last_err
+        cur.wait_stream(side)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, mix_wav, spk_idx):
+        self.wav.copy_(mix_wav, non_blocking=True)
+        self.idx.copy_(spk_idx, non_blocking=True)
+        return self.replay()
+
+    def check_index(self):
+        if int(self.err.item()):
+            raise IndexError('index out of range in self')
+
+
 class HostPipeline(object):
     """Waveforms in pinned HOST memory -> separated waveforms in pinned HOST memory, with the H2D copy of
     batch i+1 and the D2H copy of batch i-1 overlapped with the kernels of batch i (three streams, `depth`
@@ -85,17 +129,24 @@ class HostPipeline(object):
         pipe = HostPipeline(sep, B, L, S)
         for h_wav, h_idx, h_out in batches: pipe.submit(h_wav, h_idx, h_out)
         pipe.drain()            # all h_out buffers are complete after this
-    Each in-flight step needs its own h_out buffer (rotate >= depth of them)."""
+    Each in-flight step needs its own h_out buffer (rotate >= depth of them).  With `graphs=True` (default) every
+    device slot owns a `GraphedSeparator`: a step is two async copies and one graph launch."""
 
-    def __init__(self, separator, B, L, S, depth=2, device=None):
+    def __init__(self, separator, B, L, S, depth=2, device=None, graphs=True):
         self.sep = separator
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.depth = depth
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.d_wav = [torch.empty(B, L, device=dev, dtype=torch.float32) for _ in range(depth)]
-        self.d_idx = [torch.empty(B, S, device=dev, dtype=torch.int64) for _ in range(depth)]
+        self.gs = [GraphedSeparator(separator, B, L, S, device=dev) for _ in range(depth)] if graphs else None
+        if graphs:
+            self.d_wav = [g.wav for g in self.gs]
+            self.d_idx = [g.idx for g in self.gs]
+        else:
+            self.d_wav = [torch.empty(B, L, device=dev, dtype=torch.float32) for _ in range(depth)]
+            self.d_idx = [torch.empty(B, S, device=dev, dtype=torch.int64) for _ in range(depth)]
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = torch.cuda.Event()
         self.count = 0
 
@@ -109,12 +160,18 @@ class HostPipeline(object):
             self.d_idx[k].copy_(h_idx, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         cur.wait_event(self.ev_in[k])
-        out = self.sep.separate(self.d_wav[k], self.d_idx[k], check_index=False)
+        if self.gs is not None:
+            cur.wait_event(self.ev_copied[k])              # slot k's static output has left for the host
+            out = self.gs[k].replay()
+        else:
+            out = self.sep.separate(self.d_wav[k], self.d_idx[k], check_index=False)
         self.ev_done[k].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_done[k])
             h_out.copy_(out, non_blocking=True)
-            out.record_stream(self.s_out)
+            if self.gs is None:
+                out.record_stream(self.s_out)
+            self.ev_copied[k].record(self.s_out)
             self.ev_out.record(self.s_out)
         return h_out
 

@@ -377,3 +377,40 @@ def test_full_size_properties(cuda):
     assert (swapped - full['wav'][:32].flip(1)).abs().max().item() < 2e-5 * full['wav'].abs().max().item() + 1e-6
     m = full['masks']
     assert m.min().item() > 0.0 and m.max().item() < 1.0 and not torch.isnan(full['wav']).any().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cplx', [False, True])
+def test_graphed_separator_and_host_pipeline_equal_eager(cuda, cplx):
+    """The CUDA-graph replay of the step (GraphedSeparator, and HostPipeline's graph slots) returns exactly what
+    the eager launches return, batch after batch, and its index check still fires."""
+    import dl4ss_b200 as d
+    B, L, S = 12, 8000, 2
+    cell = 'gru' if cplx else 'lstm'
+    _, ours = build_pair(cell, 2, 129, 63, cplx)
+    try:
+        sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+        g = torch.Generator(device='cuda').manual_seed(5)
+        wavs = [torch.randn(B, L, device=cuda, generator=g) * 0.3 for _ in range(3)]
+        idxs = [torch.sort(torch.stack([torch.randperm(101)[:S] for _ in range(B)]), 1)[0].to(cuda) for _ in range(3)]
+        eager = [sep.separate(w, i).clone() for w, i in zip(wavs, idxs)]
+        gs = d.GraphedSeparator(sep, B, L, S)
+        for w, i, e in zip(wavs, idxs, eager):
+            out = gs(w, i)
+            assert torch.allclose(out, e, rtol=0, atol=0, equal_nan=True)
+            gs.check_index()
+        bad = idxs[0].clone()
+        bad[0, 0] = 1000
+        gs(wavs[0], bad)
+        with pytest.raises(IndexError):
+            gs.check_index()
+        pipe = d.HostPipeline(sep, B, L, S, depth=2)
+        h_out = [torch.empty(B, S, eager[0].shape[-1]).pin_memory() for _ in range(3)]
+        for k in range(3):
+            pipe.submit(wavs[k].cpu().pin_memory(), idxs[k].cpu().pin_memory(), h_out[k])
+        pipe.drain()
+        torch.cuda.synchronize()
+        for k in range(3):
+            assert torch.allclose(h_out[k], eager[k].cpu(), rtol=0, atol=0, equal_nan=True)
+    finally:
+        d.config.is_ComlexMask = 0
