@@ -195,6 +195,16 @@ int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float *mix, cons
 int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
                      float *src_out, float *mix_out, void *stream);
 
+/* ---- n2: short-lag cross-correlations for on-device BSS-Eval -----------------------------------
+ * Replaces the FFT correlations inside mir_eval.separation.bss_eval_sources (`_compute_reference_correlations`,
+ * `_compute_projection_filters`; called at Torch_multi/bss_test.py:55 on wav files read back from disk).
+ *   out[b, i, j, k] = sum_m x[b, i, m] * y[b, j, m + lag0 + k],  k in [0, nlags),  y taken as 0 outside [0, N)
+ * x [B,Sx,N], y [B,Sy,N] fp32 ; out [B,Sx,Sy,nlags] fp64 (products and sums in double).  The Gram matrix of the
+ * 512-tap projection is G[(i,a),(j,c)] = out_ref_ref[b,i,j, flen-1 + a - c] (lag0 = -(flen-1), nlags = 2*flen-1)
+ * and its right-hand side D[(i,a)] = out_ref_est[b,i,e,a] (lag0 = 0, nlags = flen). */
+int dl4ss_xcorr_f64(const float *x, const float *y, int B, int Sx, int Sy, int N, int nlags, int lag0,
+                    double *out, void *stream);
+
 /* ---- training step, backward side -----------------------------------------------------------
  * loss = l0 + 0.5*l1 (real; EvalVer.py:641,659-666) or l_re + l_im (cRM; cRM_EvalVer.py:741-743).
  * dl4ss_mask_loss_bwd: dmask = d(loss)/d(mask), same layout as mask.
