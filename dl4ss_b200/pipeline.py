@@ -75,6 +75,30 @@ class Separator(object):
 
     __call__ = separate
 
+    def recursive_extract(self, mix_feas, classifier, steps=3, alpha=-0.5):
+        """Recursive extract-and-subtract inference (TDAA_beta/main_run_sstune_RecuVer.py:32-79,480-494; the
+        reference runs it at batch size 1 through numpy): per step `classifier` (MIX_SPEECH_classifier) +
+        `top_k_mask(., alpha, 1)` name the most probable remaining speaker of every utterance, the mask path
+        predicts that speaker's spectrogram from the current features, and the prediction is subtracted from the
+        features.  Everything stays on the device, the whole batch advances together.
+        mix_feas [B,T,F] -> (predict_multi_map [B,steps,T,F], speakers int64 [B,steps])."""
+        if self.complex_mask:
+            raise NotImplementedError('the recursive variant exists for real masks only (RecuVer.py)')
+        with torch.no_grad():
+            now = mix_feas.contiguous().clone()
+            B, T, F = now.shape
+            preds = torch.empty(B, steps, T, F, device=now.device, dtype=torch.float32)
+            spk = torch.empty(B, steps, device=now.device, dtype=torch.int64)
+            for k in range(steps):
+                prob = classifier(now)
+                sel = M.top_k_mask(prob, alpha, 1)                 # exactly one 1 per row when alpha < 0
+                idx = sel.argmax(1, keepdim=True)
+                masks = self.masks(now, idx, check_index=False)    # [B,1,T,F]
+                torch.mul(masks[:, 0], now, out=preds[:, k])
+                spk[:, k] = idx[:, 0]
+                now = now - preds[:, k]
+        return preds, spk
+
 
 class GraphedSeparator(object):
     """The whole waveform -> separated-waveforms step of a `Separator` for one fixed (B, L, S), captured ONCE in a

@@ -199,6 +199,26 @@ def top_k_mask(batch_pro, alpha, top_k):
     return final
 
 
+def recursive_extract_ref(config, classifier, mix_layer, emb_layer, att_layer, adj_layer, mix_feas, steps=3, alpha=-0.5):
+    """Recursive extract-and-subtract inference, batched restatement of
+    TDAA_beta/main_run_sstune_RecuVer.py:32-79 (`model_step_output`, test_mode: top_k = 1, alpha = -0.5) and the
+    loop at :480-494: per step the classifier names the most probable remaining speaker, the attention path
+    predicts that speaker's magnitude spectrogram from the CURRENT features, and the prediction is subtracted
+    from the features before the next step.  mix_feas [B,T,F] -> (predict [B,steps,T,F], speakers [B,steps])."""
+    now = mix_feas.clone()
+    preds, spk = [], []
+    for _ in range(steps):
+        prob = classifier(now)
+        mask = top_k_mask(prob, alpha, 1)
+        idx = np.stack([np.where(line == 1)[0] for line in mask.numpy()])          # [B,1]
+        out = forward_ref(config, mix_layer, emb_layer, att_layer, adj_layer, now, idx)
+        step_pred = out['predict'][:, 0]
+        preds.append(step_pred)
+        spk.append(idx[:, 0])
+        now = now - step_pred
+    return torch.stack(preds, 1), np.stack(spk, 1)
+
+
 # --------------------------------------------------------------------------------------
 def forward_ref(config, mix_layer, emb_layer, att_layer, adj_layer, mix_feas, spk_idx, mix_mag=None):
     """The eval/train forward glue: features + speaker ids -> masks and predicted spectra.
