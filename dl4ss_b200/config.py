@@ -51,6 +51,11 @@ RNN_TENSOR_CORES = True
 # (launch bound: one library GEMM + one gate kernel per time step) from a CUDA graph captured on first use.
 TRAIN_CUDA_GRAPHS = True
 
+# Not in the reference: walk the T-step BPTT chain of a layer inside ONE persistent kernel (dl4ss_rnn_layer_bwd:
+# W_hh slice resident in shared memory, gate gradients exchanged through L2) when H is supported; False (or an
+# unsupported H) walks it with one library GEMM + one gate kernel per time step (dl4ss_rnn_bwd_step).
+TRAIN_PERSISTENT_BPTT = True
+
 # Not in the reference: run the dense contractions of the backward pass (dW = dY^T X, dX = dY W) on the tcgen05
 # bf16x3 projection kernel; False leaves them to the library GEMM (cuBLAS fp32).
 TRAIN_TC_GEMMS = True

@@ -1,0 +1,316 @@
+// dl4ss_rnn_layer_bwd : the T-step BPTT chain of one bidirectional LSTM / GRU layer as ONE persistent kernel.
+//
+// Replaces what autograd does for nn.LSTM / nn.GRU under `loss.backward()` in the reference's training loop
+// (TDAA_beta/main_run_sstune_EvalVer.py:673 ; cRM: TDAA_beta/main_run_sstune_cRM_EvalVer.py:751): per time step,
+// walking each direction's forward order in reverse,
+//     dh_t   = dy_t + dgates_{next} * W_hh            ([B,G*H] x [G*H,H], the only dense product on the chain)
+//     dgates = gate arithmetic(dh_t, saved gates / cells, carried dc or dh*z)
+// The weight / input gradients (dW_ih, dW_hh, dx) are large GEMMs over the saved dgates and run after the chain
+// on the tensor-core projection kernel; only the chain itself is latency bound, so it lives here:
+//   * a CTA owns (direction, tile of BW_BT utterances, slice of BW_HS hidden units).  The slice's columns of W_hh
+//     (transposed: one row of G*H floats per unit) stay in shared memory for all T steps; the carried state
+//     (LSTM dc*f, GRU dh*z) of its cells stays in registers of the cell's owner thread;
+//   * per step the CTA reads the previous step's recurrent-side gate gradients of its tile -- the [B,T,2,G*H]
+//     gradient array the weight GEMMs need anyway is the exchange buffer, freshly written by the sibling slices and
+//     still in L2 -- with cp.async.cg, accumulates dh for its BW_BT x BW_HS cells on the fp32 pipe, applies the
+//     gate arithmetic and writes this step's gate gradients;
+//   * the product is register tiled 4 utterances x 5 units per lane (9 conflict-free 128-bit shared-memory loads feed
+//     80 FMAs), the 16 tiles of the cell block sit in every warp, K = G*H is split over the warps and two half-warps,
+//     partial sums meet through one shuffle and a shared-memory reduction by the owner threads;
+//   * siblings of a (direction, tile) group synchronise through one L2 counter (release / acquire); groups never wait
+//     on each other; the launch is cooperative so the waits cannot deadlock.
+#include "common.cuh"
+
+namespace dl4ss {
+
+constexpr int BW_BT = 16;                 // utterances per tile
+constexpr int BW_HS = 20;                 // hidden units per slice
+constexpr int BW_CELLS = BW_BT * BW_HS;   // 320 cells per CTA, one owner thread each
+constexpr int BW_NW = 20;                 // warps
+constexpr int BW_THREADS = 32 * BW_NW;
+constexpr int BW_RB = 4, BW_RU = 5;       // register tile: rows {rb + 4i}, units {ub + 4j}
+constexpr int BW_CTR_STRIDE = 64;         // one 256-byte line per group counter
+
+struct RnnBwdParams {
+    const float *dy;        // [B,T,2H]
+    const float *whh;       // [2,G*H,H]
+    const float *gates;     // [B,T,2,G*H] saved activations
+    const float *cells;     // [B,T,2,H]  LSTM c_t | GRU W_hn h + b_hn
+    const float *y;         // [B,T,2H] layer output (GRU: h_{t-1})
+    float *dgx;             // [B,T,2,G*H] d/d(xproj)
+    float *dgh;             // GRU: d/d(W_hh h + b_hh); LSTM: null (= dgx)
+    unsigned *counters;     // [2 * tiles] * BW_CTR_STRIDE
+    int B, T, H, GHP;
+    int b_begin, batch_tiles, nslices;
+};
+
+__device__ __forceinline__ void bw_cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ unsigned bw_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int CELL>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+rnn_bwd_kernel(const RnnBwdParams p) {
+    constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+    extern __shared__ __align__(16) float smem[];
+    const int H = p.H, T = p.T, GHP = p.GHP;
+    const int GH = G * H;
+    const int nquads = GH >> 2;
+    float *Wt = smem;                                   // [BW_HS][GHP]   Wt[j][k] = W_hh[k][u0 + j]
+    float *dg = Wt + (size_t)BW_HS * GHP;               // [BW_BT][GHP]   previous step's recurrent-side gate grads
+    float *part = dg + (size_t)BW_BT * GHP;             // [BW_NW][BW_CELLS] partial sums per warp
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int bid = blockIdx.x;
+    const int slice = bid % p.nslices; bid /= p.nslices;
+    const int bt = bid % p.batch_tiles;
+    const int dir = bid / p.batch_tiles;
+    const int row0 = p.b_begin + bt * BW_BT;
+    const int u0 = slice * BW_HS;
+    unsigned *counter = p.counters + (size_t)(dir * p.batch_tiles + bt) * BW_CTR_STRIDE;
+    const float *dgr = (CELL == DL4SS_CELL_GRU) ? p.dgh : p.dgx;   // what the recurrent product consumes
+
+    // ---- resident transposed W_hh slice; zeroed exchange tile (rows beyond B and the pad columns stay zero)
+    {
+        const float *wsrc = p.whh + (size_t)dir * GH * H + u0;
+        for (int i = tid; i < GH * BW_HS; i += BW_THREADS) {
+            const int k = i / BW_HS, j = i - k * BW_HS;
+            Wt[(size_t)j * GHP + k] = __ldg(wsrc + (size_t)k * H + j);
+        }
+        for (int i = tid; i < BW_HS * (GHP - GH); i += BW_THREADS) {
+            const int j = i / (GHP - GH), k = GH + i - j * (GHP - GH);
+            Wt[(size_t)j * GHP + k] = 0.f;
+        }
+        for (int i = tid; i < BW_BT * GHP; i += BW_THREADS) dg[i] = 0.f;
+    }
+    __syncthreads();
+
+    // product mapping: lane = (ksub, rb, ub); tile rows rb + 4i (i < 4), units ub + 4j (j < 5)
+    const int ub = lane & 3, rb = (lane >> 2) & 3, ksub = lane >> 4;
+    const float *dgl = dg + (size_t)rb * GHP;
+    const float *wl = Wt + (size_t)ub * GHP;
+    // owner mapping: thread -> cell (r, j)
+    const bool owner = tid < BW_CELLS;
+    const int orow = tid / BW_HS, oj = tid - orow * BW_HS;
+    const int ob = row0 + orow;
+    const bool oval = owner && ob < p.B;
+    const int ou = u0 + oj;
+    float carry = 0.f;
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? s : (T - 1 - s);               // backward walks the forward order in reverse
+        const int tp = dir ? t + 1 : t - 1;                // the step the forward pass came from
+        const int tl = dir ? t - 1 : t + 1;                // the step this chain processed last
+        const bool has_prev = (tp >= 0 && tp < T);
+
+        // operands of the gate arithmetic do not depend on the chain: fetch them before waiting on it
+        float dyv = 0.f, gv[G], cv = 0.f, pv = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gv[g] = 0.f;
+        const size_t row = ((size_t)ob * T + t) * 2 + dir;
+        if (oval) {
+            dyv = __ldg(p.dy + ((size_t)ob * T + t) * 2 * H + (size_t)dir * H + ou);
+#pragma unroll
+            for (int g = 0; g < G; ++g) gv[g] = __ldg(p.gates + row * GH + (size_t)g * H + ou);
+            cv = __ldg(p.cells + row * H + ou);
+            if (has_prev) {
+                if (CELL == DL4SS_CELL_LSTM) pv = __ldg(p.cells + (((size_t)ob * T + tp) * 2 + dir) * H + ou);
+                else pv = __ldg(p.y + ((size_t)ob * T + tp) * 2 * H + (size_t)dir * H + ou);
+            }
+        }
+
+        float dh = dyv;
+        if (s > 0) {
+            if (tid == 0) {
+                const unsigned want = (unsigned)p.nslices * (unsigned)s;
+                while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
+            }
+            __syncthreads();
+            for (int i = tid; i < BW_BT * nquads; i += BW_THREADS) {
+                const int r = i / nquads, q = i - r * nquads;
+                const int b = row0 + r;
+                if (b < p.B)
+                    bw_cp_async16(dg + (size_t)r * GHP + 4 * q, dgr + (((size_t)b * T + tl) * 2 + dir) * GH + 4 * q);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
+
+            float acc[BW_RB][BW_RU];
+#pragma unroll
+            for (int i = 0; i < BW_RB; ++i)
+#pragma unroll
+                for (int j = 0; j < BW_RU; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+            for (int q = 2 * warp + ksub; q < nquads; q += 2 * BW_NW) {
+                float4 a[BW_RB], w[BW_RU];
+#pragma unroll
+                for (int i = 0; i < BW_RB; ++i) a[i] = *reinterpret_cast<const float4 *>(dgl + (size_t)(4 * i) * GHP + 4 * q);
+#pragma unroll
+                for (int j = 0; j < BW_RU; ++j) w[j] = *reinterpret_cast<const float4 *>(wl + (size_t)(4 * j) * GHP + 4 * q);
+#pragma unroll
+                for (int i = 0; i < BW_RB; ++i)
+#pragma unroll
+                    for (int j = 0; j < BW_RU; ++j) {
+                        float v = acc[i][j];
+                        v = fmaf(a[i].x, w[j].x, v);
+                        v = fmaf(a[i].y, w[j].y, v);
+                        v = fmaf(a[i].z, w[j].z, v);
+                        v = fmaf(a[i].w, w[j].w, v);
+                        acc[i][j] = v;
+                    }
+            }
+            // the two half-warps meet, then each half writes half of the tile's partial sums
+            float *pw = part + (size_t)warp * BW_CELLS;
+#pragma unroll
+            for (int i = 0; i < BW_RB; ++i)
+#pragma unroll
+                for (int j = 0; j < BW_RU; ++j) {
+                    const float v = acc[i][j] + __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+                    if (((i * BW_RU + j) & 1) == ksub) pw[(rb + 4 * i) * BW_HS + ub + 4 * j] = v;
+                }
+            __syncthreads();
+            if (owner) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < BW_NW; ++w) v += part[w * BW_CELLS + tid];
+                dh += v;
+            }
+        }
+
+        if (oval) {
+            float *ox = p.dgx + row * GH + ou;
+            if constexpr (CELL == DL4SS_CELL_LSTM) {
+                const float ig = gv[0], fg = gv[1], gg = gv[2], og = gv[3];
+                const float tc = tanhf(cv);
+                const float dc = fmaf(dh * og, 1.0f - tc * tc, carry);
+                const float dai = dc * gg * ig * (1.0f - ig);
+                const float daf = dc * pv * fg * (1.0f - fg);
+                const float dag = dc * ig * (1.0f - gg * gg);
+                const float dao = dh * tc * og * (1.0f - og);
+                carry = dc * fg;
+                __stcg(ox, dai); __stcg(ox + H, daf); __stcg(ox + 2 * (size_t)H, dag); __stcg(ox + 3 * (size_t)H, dao);
+            } else {
+                dh += carry;                                   // the z * h_{t-1} path
+                const float rg = gv[0], zg = gv[1], ng = gv[2];
+                const float hn = cv;                           // W_hn h + b_hn saved by the forward kernel
+                const float dn = dh * (1.0f - zg);
+                const float dan = dn * (1.0f - ng * ng);
+                const float dar = dan * hn * rg * (1.0f - rg);
+                const float daz = dh * (pv - ng) * zg * (1.0f - zg);
+                const float dhn = dan * rg;
+                carry = dh * zg;
+                float *oh = p.dgh + row * GH + ou;
+                __stcg(ox, dar); __stcg(ox + H, daz); __stcg(ox + 2 * (size_t)H, dan);
+                __stcg(oh, dar); __stcg(oh + H, daz); __stcg(oh + 2 * (size_t)H, dhn);
+            }
+        }
+        if (s + 1 < T) {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
+            }
+        }
+    }
+}
+
+static int bwd_ghp(int GH) { return GH + ((8 - GH % 32 + 32) % 32); }   // row pitch == 8 (mod 32) floats: the 8 distinct
+                                                                         // 16-byte chunks of a warp load tile the 32 banks
+
+template <int CELL>
+static int launch_rnn_bwd(RnnBwdParams p, int rows_left, cudaStream_t st, int *launched_rows) {
+    constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+    p.GHP = bwd_ghp(G * p.H);
+    p.nslices = p.H / BW_HS;
+    const size_t smem = ((size_t)(BW_HS + BW_BT) * p.GHP + (size_t)BW_NW * BW_CELLS) * sizeof(float);
+    if (smem > 227 * 1024) {
+        set_error("rnn_layer_bwd: H=%d needs %zu B of shared memory per CTA", p.H, smem);
+        return DL4SS_EUNSUPPORTED;
+    }
+    auto kern = rnn_bwd_kernel<CELL>;
+    DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DL4SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BW_THREADS, smem));
+    const int max_tiles = per_sm * sm_count() / (2 * p.nslices);
+    if (max_tiles < 1) {
+        set_error("rnn_layer_bwd: %d co-resident CTAs cannot hold one tile (%d slices x 2 directions)",
+                  per_sm * sm_count(), p.nslices);
+        return DL4SS_EUNSUPPORTED;
+    }
+    int tiles = cdiv(rows_left, BW_BT);
+    if (tiles > max_tiles) tiles = max_tiles;
+    p.batch_tiles = tiles;
+    *launched_rows = tiles * BW_BT;
+    void *args[] = {(void *)&p};
+    DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * tiles * p.nslices), dim3(BW_THREADS), args, smem, st));
+    count_launch();
+    return DL4SS_OK;
+}
+
+static bool rnn_bwd_supported(int H, int cell) {
+    if (!(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU)) return false;
+    if (H < BW_HS || H % BW_HS != 0) return false;
+    const int G = (cell == DL4SS_CELL_LSTM) ? 4 : 3;
+    const size_t smem = ((size_t)(BW_HS + BW_BT) * bwd_ghp(G * H) + (size_t)BW_NW * BW_CELLS) * sizeof(float);
+    return smem <= 227 * 1024;
+}
+
+}  // namespace dl4ss
+
+using namespace dl4ss;
+
+extern "C" int dl4ss_rnn_bwd_supported(int H, int cell) { return rnn_bwd_supported(H, cell) ? 1 : 0; }
+
+extern "C" size_t dl4ss_rnn_bwd_workspace_bytes(int B, int T, int H, int cell) {
+    (void)T; (void)H; (void)cell;
+    if (B <= 0) return 256;
+    return (size_t)2 * cdiv(B, BW_BT) * BW_CTR_STRIDE * sizeof(unsigned);
+}
+
+extern "C" int dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, const float *gates_save,
+                                   const float *cell_save, const float *y, float *dgx, float *dgh, int B, int T, int H,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_bwd: bad cell %d", cell);
+    DL4SS_CHECK_ARG(dy && whh && gates_save && cell_save && dgx, "rnn_layer_bwd: null operand");
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || (y && dgh), "rnn_layer_bwd: GRU needs y and dgh");
+    DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1, "rnn_layer_bwd: bad B/T/H %d/%d/%d", B, T, H);
+    if (!rnn_bwd_supported(H, cell)) {
+        set_error("rnn_layer_bwd: H=%d unsupported (needs a multiple of %d whose W_hh slice fits shared memory); "
+                  "use dl4ss_rnn_bwd_step", H, BW_HS);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0) return DL4SS_OK;
+    const size_t need = dl4ss_rnn_bwd_workspace_bytes(B, T, H, cell);
+    if (!workspace || workspace_bytes < need) {
+        set_error("rnn_layer_bwd: workspace %zu B < %zu B", workspace_bytes, need);
+        return DL4SS_EWORKSPACE;
+    }
+    DL4SS_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "rnn_layer_bwd: workspace must be 256-byte aligned");
+    DL4SS_CHECK_ARG((((uintptr_t)dgx) & 15) == 0 && (!dgh || (((uintptr_t)dgh) & 15) == 0),
+                    "rnn_layer_bwd: dgx / dgh must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    DL4SS_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    RnnBwdParams p;
+    p.dy = dy; p.whh = whh; p.gates = gates_save; p.cells = cell_save; p.y = y; p.dgx = dgx; p.dgh = dgh;
+    p.B = B; p.T = T; p.H = H; p.GHP = 0; p.batch_tiles = 0; p.nslices = 0;
+    unsigned *ctr = (unsigned *)workspace;
+    int b0 = 0;
+    while (b0 < B) {
+        p.b_begin = b0;
+        p.counters = ctr;
+        int done = 0;
+        int rc = (cell == DL4SS_CELL_LSTM) ? launch_rnn_bwd<DL4SS_CELL_LSTM>(p, B - b0, st, &done)
+                                           : launch_rnn_bwd<DL4SS_CELL_GRU>(p, B - b0, st, &done);
+        if (rc) return rc;
+        ctr += (size_t)2 * (done / BW_BT) * BW_CTR_STRIDE;
+        b0 += done;
+    }
+    return DL4SS_OK;
+}

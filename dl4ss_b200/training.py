@@ -17,6 +17,8 @@ Utterances shard by batch across ranks: every rank runs the step on 
 loss normalised by the GLOBAL element count, then one all-reduce (sum) of the flat fp32 gradient
 bucket reproduces the global-batch MSELoss gradients on every rank.
 """
+import ctypes
+
 import torch
 from torch import nn
 
@@ -248,6 +250,19 @@ class TrainStep(object):
                                         _lib.stream())
             _lib.check(rc, 'dl4ss_rnn_bwd_step')
 
+    def _bptt_persistent(self, cell, st, dy, whh, B, T, H):
+        """The T-step BPTT chain of one layer as one persistent kernel (csrc/rnn_bwd.cu)."""
+        lib = _lib.load()
+        need = lib.dl4ss_rnn_bwd_workspace_bytes(B, T, H, cell)
+        ws = st.get('bwd_ws')
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, device=dy.device, dtype=torch.uint8)
+            st['bwd_ws'] = ws
+        rc = lib.dl4ss_rnn_layer_bwd(cell, _lib.ptr(dy), _lib.ptr(whh), _lib.ptr(st['gates']), _lib.ptr(st['cells']),
+                                     _lib.ptr(st['y']), _lib.ptr(st['dgx']), _lib.ptr(st['dgh']), B, T, H,
+                                     ctypes.c_void_p(ws.data_ptr()), need, _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_layer_bwd')
+
     def rnn_backward(self, ctx, dy):
         rnn = self.mix.layer
         gru = isinstance(rnn, nn.GRU)
@@ -267,12 +282,17 @@ class TrainStep(object):
                       'dgx': torch.empty(B, T, 2, G * H, device=dev), 'dgh': torch.empty(B, T, 2, G * H, device=dev) if gru else None,
                       'carry': torch.empty(2, B, H, device=dev), 'dg_cur': torch.empty(2, B, G * H, device=dev),
                       'dh_rec': torch.empty(2, B, H, device=dev), 'whh': lw['whh'], 'graph': None}
-            st['dy'].copy_(dy)
-            if use_graph:
+            persistent = bool(config.TRAIN_PERSISTENT_BPTT) and _lib.load().dl4ss_rnn_bwd_supported(H, cell) != 0
+            if persistent:
+                self._bptt_persistent(cell, st, dy, lw['whh'], B, T, H)      # the whole chain in one launch
+            elif use_graph and st['graph'] is not None:
+                st['dy'].copy_(dy)
                 st['whh'].copy_(lw['whh'])
-            if use_graph and st['graph'] is not None:
                 st['graph'].replay()
             else:
+                st['dy'].copy_(dy)
+                if use_graph:
+                    st['whh'].copy_(lw['whh'])
                 self._bptt_chain(cell, st, B, T, H)          # eager: also warms cuBLAS up before any capture
                 if use_graph and T > 4:
                     # the chain is launch bound (2 launches per time step): capture it once, replay it from now on

@@ -226,6 +226,23 @@ int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, co
                        const float *cell_save, const float *y, float *carry, float *dgx, float *dgh,
                        float *dg_cur, int B, int T, int H, void *stream);
 
+/* ---- the whole BPTT chain of one bidirectional layer as ONE persistent kernel -------------------------
+ * Replaces autograd's T sequential LSTM / GRU backward steps under `loss.backward()`
+ * (TDAA_beta/main_run_sstune_EvalVer.py:673 ; TDAA_beta/main_run_sstune_cRM_EvalVer.py:751).
+ * dy [B,T,2H] = d(loss)/d(layer output); whh [2,G*H,H] fp32 (the nn.LSTM / nn.GRU weight_hh of both directions);
+ * gates_save / cell_save / y as written by dl4ss_rnn_layer_*fwd.  Outputs: dgx [B,T,2,G*H] = d/d(xproj) and,
+ * GRU only, dgh [B,T,2,G*H] = d/d(W_hh h + b_hh) (NULL for LSTM, where it equals dgx); both 16-byte aligned.
+ * The weight / input gradients are GEMMs over these arrays (dl4ss_linear_tc_fwd on transposed operands).
+ * Supported when dl4ss_rnn_bwd_supported(H, cell) != 0 (H a multiple of 20 whose 20-unit W_hh slice fits
+ * shared memory: every reference config, H = 300); otherwise DL4SS_EUNSUPPORTED and the caller walks the
+ * chain with dl4ss_rnn_bwd_step.  workspace: dl4ss_rnn_bwd_workspace_bytes() bytes, 256-byte aligned,
+ * zero-filled by the callee (release counters). */
+int    dl4ss_rnn_bwd_supported(int H, int cell);
+size_t dl4ss_rnn_bwd_workspace_bytes(int B, int T, int H, int cell);
+int    dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, const float *gates_save,
+                           const float *cell_save, const float *y, float *dgx, float *dgh, int B, int T, int H,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,68 @@ def test_train_step_reduces_loss(cuda):
     idx = np.array([[1, 5], [2, 9], [0, 7], [3, 4]])
     losses = [step.step(opt, feas, idx, y)[0].item() for _ in range(8)]
     assert losses[-1] < losses[0]
+
+
+def _bptt_step_chain(lib, L, cell, dy, whh, gates, cells, y, B, T, H, G):
+    """The per-step form (library GEMM + dl4ss_rnn_bwd_step): the yard-stick for the persistent kernel."""
+    dev = dy.device
+    dgx = torch.zeros(B, T, 2, G * H, device=dev)
+    dgh = torch.zeros(B, T, 2, G * H, device=dev) if G == 3 else None
+    carry = torch.zeros(2, B, H, device=dev)
+    dg_cur = torch.zeros(2, B, G * H, device=dev)
+    dh_rec = torch.zeros(2, B, H, device=dev)
+    for s in range(T):
+        if s > 0:
+            torch.bmm(dg_cur, whh, out=dh_rec)
+        rc = lib.dl4ss_rnn_bwd_step(cell, s, L.ptr(dy), L.ptr(dh_rec), L.ptr(gates), L.ptr(cells), L.ptr(y),
+                                    L.ptr(carry), L.ptr(dgx), L.ptr(dgh), L.ptr(dg_cur), B, T, H, L.stream())
+        L.check(rc, 'dl4ss_rnn_bwd_step')
+    return dgx, dgh
+
+
+@pytest.mark.parametrize('cell,B,T,H', [('lstm', 5, 9, 300), ('gru', 37, 6, 300), ('lstm', 70, 4, 300),
+                                         ('gru', 16, 1, 300), ('lstm', 3, 5, 40)])
+def test_persistent_bptt_equals_step_chain(cuda, cell, B, T, H):
+    """dl4ss_rnn_layer_bwd (one persistent kernel) against the per-step chain on the same saved activations:
+    partial tiles, several tiles, more utterances than one launch holds (B=70), T=1, a small H."""
+    import ctypes
+    from dl4ss_b200 import _lib as L
+    lib = L.load()
+    G = 4 if cell == 'lstm' else 3
+    c = L.CELL_LSTM if cell == 'lstm' else L.CELL_GRU
+    assert lib.dl4ss_rnn_bwd_supported(H, c) == 1
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(B, T, 2 * H, generator=g).to(cuda)
+    whh = (torch.randn(2, G * H, H, generator=g) / H ** 0.5).to(cuda)
+    gates = torch.rand(B, T, 2, G * H, generator=g)
+    if cell == 'lstm':
+        gates[..., 2 * H:3 * H] = gates[..., 2 * H:3 * H] * 2 - 1        # g gate is a tanh
+    else:
+        gates[..., 2 * H:] = gates[..., 2 * H:] * 2 - 1                  # n gate is a tanh
+    gates = gates.to(cuda)
+    cells = torch.randn(B, T, 2, H, generator=g).to(cuda)
+    y = (torch.rand(B, T, 2 * H, generator=g) * 2 - 1).to(cuda)
+    ref_x, ref_h = _bptt_step_chain(lib, L, c, dy, whh, gates, cells, y, B, T, H, G)
+    dgx = torch.full((B, T, 2, G * H), float('nan'), device=cuda)
+    dgh = torch.full((B, T, 2, G * H), float('nan'), device=cuda) if G == 3 else None
+    need = lib.dl4ss_rnn_bwd_workspace_bytes(B, T, H, c)
+    ws = torch.empty(need, device=cuda, dtype=torch.uint8)
+    rc = lib.dl4ss_rnn_layer_bwd(c, L.ptr(dy), L.ptr(whh), L.ptr(gates), L.ptr(cells), L.ptr(y), L.ptr(dgx),
+                                 L.ptr(dgh), B, T, H, ctypes.c_void_p(ws.data_ptr()), need, L.stream())
+    L.check(rc, 'dl4ss_rnn_layer_bwd')
+    torch.cuda.synchronize()
+    scale = ref_x.abs().max().item()
+    assert (dgx - ref_x).abs().max().item() < 2e-5 * scale
+    if G == 3:
+        assert (dgh - ref_h).abs().max().item() < 2e-5 * scale
+
+
+def test_persistent_bptt_unsupported_is_loud(cuda):
+    from dl4ss_b200 import _lib as L
+    lib = L.load()
+    assert lib.dl4ss_rnn_bwd_supported(301, L.CELL_LSTM) == 0
+    assert lib.dl4ss_rnn_bwd_supported(600, L.CELL_LSTM) == 0          # 20 x 2400 fp32 W slice + tile do not fit
+    x = torch.zeros(16, device=cuda)
+    rc = lib.dl4ss_rnn_layer_bwd(L.CELL_LSTM, L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), None, L.ptr(x), None, 1, 1, 301,
+                                 None, 0, L.stream())
+    assert rc != 0 and b'unsupported' in lib.dl4ss_last_error()
