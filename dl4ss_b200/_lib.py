@@ -42,6 +42,7 @@ SIGNATURES = {
     'dl4ss_split_bf16': (c_i, [c_p, c_i, c_ll, c_i, c_p, c_p]),
     'dl4ss_split_bf16_t': (c_i, [c_p, c_ll, c_i, c_i, c_p, c_p]),
     'dl4ss_linear_tc_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    'dl4ss_linear_tc_splitk_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     'dl4ss_emb_attn_mask_tc_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_attn_dot_fwd': (c_i, [c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_speaker_query_fwd': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     'dl4ss_attn_dot_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     'dl4ss_rnn_bwd_step': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     'dl4ss_rnn_bwd_supported': (c_i, [c_i, c_i]),
+    'dl4ss_rnn_bwd_set_trace': (None, [c_p, c_i]),
     'dl4ss_rnn_bwd_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'dl4ss_rnn_layer_bwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_sz, c_p]),
     'dl4ss_mask_loss_fwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),

@@ -93,6 +93,7 @@ struct EpiPlain {
     float *C;
     const float *bias;
     int ldc;
+    int atomic;          // split-K launch: partial tiles are summed into a zeroed C with red.add (ACT must be NONE)
 };
 struct EpiAttn {
     const float *bias;   // [F*E]
@@ -159,7 +160,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT> &e, uint32_t t
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = apply_act<ACT>(stage[row * TC_STAGE_PITCH + col + k] + bz[k]);
             float *dst = e.C + (size_t)m * e.ldc + n + col;
-            if (vec && n + col + 3 < N) {
+            if (e.atomic) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (n + col + k < N) atomicAdd(dst + k, o[k]);
+            } else if (vec && n + col + 3 < N) {
                 *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
@@ -227,11 +231,23 @@ __device__ __forceinline__ void epilogue_tile(const EpiAttn &e, uint32_t taddr, 
     }
 }
 
+// the epilogue a K split of a tile runs: only split 0 adds the bias
+template <int ACT>
+__device__ __forceinline__ EpiPlain<ACT> epi_of_split(const EpiPlain<ACT> &e, int ks) {
+    EpiPlain<ACT> r = e;
+    if (ks != 0) r.bias = nullptr;
+    return r;
+}
+__device__ __forceinline__ const EpiAttn &epi_of_split(const EpiAttn &e, int) { return e; }
+
 // ------------------------------------------------------------------------------------------ kernel
+// Work items are (tile, K split): nsplit > 1 cuts the k-blocks of every tile into nsplit ranges whose partial
+// accumulators meet in C through fp32 atomics -- for the backward contractions over B*T rows whose M x N output is a
+// handful of tiles (dW = dY^T X: 57 or 20 tiles on 148 SMs).
 template <typename Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int M, int N, int kblocks, int m_tiles, int n_tiles, const Epi epi) {
+                   int M, int N, int kblocks, int m_tiles, int n_tiles, int nsplit, const Epi epi) {
     constexpr int NSTEP = EpiTraits<Epi>::NSTEP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -240,7 +256,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TSTAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = m_tiles * n_tiles;
+    const int total_work = m_tiles * n_tiles * nsplit;
+    const int kper = (kblocks + nsplit - 1) / nsplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
@@ -261,9 +278,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int tile = w / nsplit, ks = w - tile * nsplit;
                 const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *st = tiles + (size_t)stage * TSTAGE_BYTES;
                     mbar_expect_tx(&full[stage], TSTAGE_BYTES);
@@ -279,11 +298,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (lane == 0) {
                         constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int ks = w % nsplit;
+                const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + acc * TBN;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)stage * TSTAGE_BYTES);
@@ -291,7 +312,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     const uint64_t b_hi = umma_desc_sw128(sa + 2 * TA_BYTES), b_lo = umma_desc_sw128(sa + 2 * TA_BYTES + TB_BYTES);
 #pragma unroll
                     for (int k = 0; k < TBK / 16; ++k) {        // +32 B per 16-element k step (>>4 = 2)
-                        umma_bf16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, ((kb - kb0) | k) != 0);
                         umma_bf16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
                         umma_bf16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
                     }
@@ -309,12 +330,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float *stage = reinterpret_cast<float *>(tiles + (size_t)TSTAGES * TSTAGE_BYTES + 256) +
                        (size_t)((part * 4 + quarter) % TC_STORE_WARPS) * 32 * TC_STAGE_PITCH;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int tile = w / nsplit, ks = w - tile * nsplit;
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TBN;
-            epilogue_tile(epi, taddr, m0 + quarter * 32, n0, M, N, part, lane, stage);
+            epilogue_tile(epi_of_split(epi, ks), taddr, m0 + quarter * 32, n0, M, N, part, lane, stage);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -364,9 +386,23 @@ static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int
     return make_bf16_map(map, planes, 3, dims, strides, box);
 }
 
+// K splits that minimise (waves of work items) x (k-blocks per item) on `sms` SMs; every split keeps >= 4 k-blocks
+// and no split is empty
+static int pick_ksplit(long long tiles, int kblocks, int sms) {
+    int best = 1;
+    long long best_cost = cdivll(tiles, sms) * kblocks;
+    for (int ns = 2; ns <= 32 && kblocks / ns >= 4; ++ns) {
+        const int kper = cdiv(kblocks, ns);
+        if ((long long)kper * (ns - 1) >= kblocks) continue;          // the last split would be empty
+        const long long cost = cdivll(tiles * ns, sms) * kper;
+        if (cost * 100 < best_cost * 95) { best_cost = cost; best = ns; }   // a further split must buy >= 5 %
+    }
+    return best;
+}
+
 template <typename Epi>
 static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, int K, int n_tiles, const Epi &epi,
-                     cudaStream_t st) {
+                     cudaStream_t st, int nsplit = 1) {
     const int Kp = (K + TBK - 1) / TBK * TBK;
     CUtensorMap ma, mb;
     int rc = make_plane_map(&ma, a_planes, M, Kp, TBM);
@@ -374,12 +410,12 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
     rc = make_plane_map(&mb, w_planes, N, Kp, TBN);        // rows past N (and past a tile's own rows) are ignored / zero
     if (rc) return rc;
     const int m_tiles = cdiv(M, TBM);
-    const long long total = (long long)m_tiles * n_tiles;
+    const long long total = (long long)m_tiles * n_tiles * nsplit;
     int grid = sm_count();
     if (total < grid) grid = (int)total;
     auto kern = gemm_bf16x3_kernel<Epi>;
     DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, epi);
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, nsplit, epi);
     DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel");
     return DL4SS_OK;
 }
@@ -433,6 +469,18 @@ extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, c
     if (act == DL4SS_ACT_SIGMOID)
         return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_SIGMOID>{C, bias, ldc}, (cudaStream_t)stream);
     return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream);
+}
+
+extern "C" int dl4ss_linear_tc_splitk_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
+                                          int ldc, int M, int N, int K, void *stream) {
+    DL4SS_CHECK_ARG(a_planes && w_planes && C, "linear_tc_splitk_fwd: null operand");
+    DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "linear_tc_splitk_fwd: bad M/N/K/ldc %d/%d/%d/%d", M, N, K, ldc);
+    if (M == 0) return DL4SS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = cdiv(N, TBN);
+    const int ns = pick_ksplit((long long)cdiv(M, TBM) * n_tiles, cdiv(K, TBK), sm_count());
+    if (ns > 1) DL4SS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+    return launch_tc(a_planes, w_planes, M, N, K, n_tiles, EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc, ns > 1 ? 1 : 0}, st, ns);
 }
 
 extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,

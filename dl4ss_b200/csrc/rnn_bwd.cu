@@ -42,7 +42,13 @@ struct RnnBwdParams {
     unsigned *counters;     // [2 * tiles] * BW_CTR_STRIDE
     int B, T, H, GHP;
     int b_begin, batch_tiles, nslices;
+    long long *trace;       // optional [steps][8] clock stamps of CTA 0 (profiling hook), else null
+    int trace_steps;
 };
+
+__device__ __forceinline__ void bw_stamp(const RnnBwdParams &p, int s, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && s < p.trace_steps) p.trace[s * 8 + slot] = clock64();
+}
 
 __device__ __forceinline__ void bw_cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -127,10 +133,12 @@ rnn_bwd_kernel(const RnnBwdParams p) {
 
         float dh = dyv;
         if (s > 0) {
+            bw_stamp(p, s, 0);
             if (tid == 0) {
                 const unsigned want = (unsigned)p.nslices * (unsigned)s;
                 while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
             }
+            bw_stamp(p, s, 1);
             __syncthreads();
             for (int i = tid; i < BW_BT * nquads; i += BW_THREADS) {
                 const int r = i / nquads, q = i - r * nquads;
@@ -141,6 +149,7 @@ rnn_bwd_kernel(const RnnBwdParams p) {
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();
+            bw_stamp(p, s, 2);
 
             float acc[BW_RB][BW_RU];
 #pragma unroll
@@ -175,7 +184,9 @@ rnn_bwd_kernel(const RnnBwdParams p) {
                     const float v = acc[i][j] + __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
                     if (((i * BW_RU + j) & 1) == ksub) pw[(rb + 4 * i) * BW_HS + ub + 4 * j] = v;
                 }
+            bw_stamp(p, s, 3);
             __syncthreads();
+            bw_stamp(p, s, 4);
             if (owner) {
                 float v = 0.f;
 #pragma unroll
@@ -212,14 +223,20 @@ rnn_bwd_kernel(const RnnBwdParams p) {
             }
         }
         if (s + 1 < T) {
+            bw_stamp(p, s, 5);
             __syncthreads();
+            bw_stamp(p, s, 6);
             if (tid == 0) {
                 __threadfence();
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
             }
+            bw_stamp(p, s, 7);
         }
     }
 }
+
+static long long *g_bwd_trace = nullptr;
+static int g_bwd_trace_steps = 0;
 
 static int bwd_ghp(int GH) { return GH + ((8 - GH % 32 + 32) % 32); }   // row pitch == 8 (mod 32) floats: the 8 distinct
                                                                          // 16-byte chunks of a warp load tile the 32 banks
@@ -266,6 +283,12 @@ static bool rnn_bwd_supported(int H, int cell) {
 
 using namespace dl4ss;
 
+// profiling hook: device buffer of steps*8 int64 receiving CTA 0's per-phase clock64() stamps (null = off)
+extern "C" void dl4ss_rnn_bwd_set_trace(void *dev_buf, int steps) {
+    g_bwd_trace = (long long *)dev_buf;
+    g_bwd_trace_steps = dev_buf ? steps : 0;
+}
+
 extern "C" int dl4ss_rnn_bwd_supported(int H, int cell) { return rnn_bwd_supported(H, cell) ? 1 : 0; }
 
 extern "C" size_t dl4ss_rnn_bwd_workspace_bytes(int B, int T, int H, int cell) {
@@ -300,6 +323,7 @@ extern "C" int dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, 
     RnnBwdParams p;
     p.dy = dy; p.whh = whh; p.gates = gates_save; p.cells = cell_save; p.y = y; p.dgx = dgx; p.dgh = dgh;
     p.B = B; p.T = T; p.H = H; p.GHP = 0; p.batch_tiles = 0; p.nslices = 0;
+    p.trace = g_bwd_trace; p.trace_steps = g_bwd_trace_steps;
     unsigned *ctr = (unsigned *)workspace;
     int b0 = 0;
     while (b0 < B) {

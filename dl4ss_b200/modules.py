@@ -78,7 +78,7 @@ def ctypes_ptr(t):
 def matmul_tn(a2d, b2d):
     """a2d^T @ b2d  ([R,Ca],[R,Cb] -> [Ca,Cb]) on tcgen05 (bf16x3): both operands transposed-split, contraction over R."""
     R = a2d.shape[0]
-    return linear_tc(split_bf16_t(a2d), split_bf16_t(b2d), None, a2d.shape[1], b2d.shape[1], R)
+    return linear_tc(split_bf16_t(a2d), split_bf16_t(b2d), None, a2d.shape[1], b2d.shape[1], R, split_k=True)
 
 
 def matmul_nn(a2d, w):
@@ -97,11 +97,18 @@ def weight_planes(w):
     return ent[2]
 
 
-def linear_tc(a_planes, w_planes, bias, M, N, K, out=None, act='none'):
-    """act(a[M,K] @ w[N,K]^T + bias) from pre-split planes on tcgen05 (bf16x3, fp32 accumulate)."""
+def linear_tc(a_planes, w_planes, bias, M, N, K, out=None, act='none', split_k=False):
+    """act(a[M,K] @ w[N,K]^T + bias) from pre-split planes on tcgen05 (bf16x3, fp32 accumulate).
+    split_k: let the kernel cut K into splits that fill the SMs when the output is only a few tiles (act 'none')."""
     lib = _lib.load()
     if out is None:
         out = torch.empty(M, N, device=a_planes.device, dtype=torch.float32)
+    if split_k and act == 'none':
+        rc = lib.dl4ss_linear_tc_splitk_fwd(_lib.ptr(a_planes, torch.bfloat16), _lib.ptr(w_planes, torch.bfloat16),
+                                            _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0), M, N, K,
+                                            _lib.stream())
+        _lib.check(rc, 'dl4ss_linear_tc_splitk_fwd')
+        return out
     a = {'none': _lib.ACT_NONE, 'tanh': _lib.ACT_TANH, 'sigmoid': _lib.ACT_SIGMOID}[act]
     rc = lib.dl4ss_linear_tc_fwd(_lib.ptr(a_planes, torch.bfloat16), _lib.ptr(w_planes, torch.bfloat16),
                                  _lib.ptr(bias, name='bias'), _lib.ptr(out), out.stride(0), M, N, K, a, _lib.stream())

@@ -155,6 +155,13 @@ int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, v
 int dl4ss_split_bf16_t(const float *x, long long ld, int R, int C, void *planes, void *stream);
 int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
                         int ldc, int M, int N, int K, int act, void *stream);
+/* Same contraction without an activation, for outputs of only a few 128x256 tiles and a long K (the backward
+ * contractions over B*T rows, dW = dY^T X): the k-blocks of every tile are cut into as many splits as fill the
+ * SMs and the partial tiles meet in C through fp32 atomic adds (C is zeroed by the callee; the summation order of
+ * the splits is not fixed, so results can differ in the last bits from run to run).  Falls back to the single-pass
+ * launch when the tiles already fill the machine. */
+int dl4ss_linear_tc_splitk_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
+                               int ldc, int M, int N, int K, void *stream);
 int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
                                const float *q, int B, int T, int F, int E, int K, int S, int mode,
                                float crm_k, float crm_c, float *mask_out, void *stream);
@@ -238,6 +245,9 @@ int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, co
  * chain with dl4ss_rnn_bwd_step.  workspace: dl4ss_rnn_bwd_workspace_bytes() bytes, 256-byte aligned,
  * zero-filled by the callee (release counters). */
 int    dl4ss_rnn_bwd_supported(int H, int cell);
+/* profiling hook: device buffer of steps*8 int64 that receives CTA 0's per-phase clock64() stamps of subsequent
+ * dl4ss_rnn_layer_bwd launches (NULL switches it off; off by default) */
+void   dl4ss_rnn_bwd_set_trace(void *dev_buf, int steps);
 size_t dl4ss_rnn_bwd_workspace_bytes(int B, int T, int H, int cell);
 int    dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, const float *gates_save,
                            const float *cell_save, const float *y, float *dgx, float *dgh, int B, int T, int H,

@@ -132,3 +132,24 @@ def test_persistent_bptt_unsupported_is_loud(cuda):
     rc = lib.dl4ss_rnn_layer_bwd(L.CELL_LSTM, L.ptr(x), L.ptr(x), L.ptr(x), L.ptr(x), None, L.ptr(x), None, 1, 1, 301,
                                  None, 0, L.stream())
     assert rc != 0 and b'unsupported' in lib.dl4ss_last_error()
+
+
+@pytest.mark.parametrize('R,Ca,Cb', [(5000, 300, 129), (777, 1200, 300), (64, 40, 7), (20032, 130, 600)])
+def test_matmul_tn_split_k(cuda, R, Ca, Cb):
+    """dW-shaped contraction a^T b over many rows and few output tiles: the split-K launch (partial tiles summed with
+    atomics) against float64, and with a bias against the single-pass launch."""
+    from dl4ss_b200 import modules as M
+    g = torch.Generator().manual_seed(R)
+    a = torch.randn(R, Ca, generator=g)
+    b = torch.randn(R, Cb, generator=g)
+    ref = a.double().t() @ b.double()
+    out = M.matmul_tn(a.to(cuda), b.to(cuda))
+    torch.cuda.synchronize()
+    assert out.shape == (Ca, Cb)
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+    bias = torch.randn(Cb, generator=g).to(cuda)
+    ap, bp = M.split_bf16_t(a.to(cuda)), M.split_bf16_t(b.to(cuda))
+    one = M.linear_tc(ap, bp, bias, Ca, Cb, R)
+    many = M.linear_tc(ap, bp, bias, Ca, Cb, R, split_k=True)
+    torch.cuda.synchronize()
+    assert (one - many).abs().max().item() < 1e-4 * ref.abs().max().item()      # single-pass fp32 accumulation over all of K is the looser of the two
