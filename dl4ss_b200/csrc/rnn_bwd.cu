@@ -19,7 +19,7 @@
 //     partial sums meet through one shuffle and a shared-memory reduction by the owner threads;
 //   * siblings of a (direction, tile) group synchronise through one L2 counter (release / acquire); groups never wait
 //     on each other; the launch is cooperative so the waits cannot deadlock.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace dl4ss {
 
@@ -235,6 +235,236 @@ rnn_bwd_kernel(const RnnBwdParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the same chain (bf16x3: operands split into bf16 hi/lo planes, three products per fp32 product,
+// fp32 accumulation).  The per-step product is [16 utterances x G*H] x [G*H x 20 units]: K = 1200 against a 16 x 20
+// output.  tcgen05 is the wrong tool for this shape -- a UMMA has K = 16 and costs ~75 cycles however small it is
+// (DESIGN.md 4), so 75 dependent k steps would take ~5.6 k cycles on the single issuing thread -- whereas warp-level
+// mma.sync.m16n8k16 spreads the k steps over 16 warps (5 k steps x 9 MMAs each) and leaves the accumulators in
+// registers: the product drops from ~6.7 k cycles on the fp32 pipe to a few hundred.  What the kernel changes around it:
+//   * W_hh^T slice resident in shared memory as bf16 hi/lo planes [2][24][pitch] (B fragments are plain 32-bit loads);
+//   * the gate gradients are exchanged as bf16 hi/lo planes (`xplanes` [2][B*T][2][GHg], the same 4 bytes per value
+//     as fp32), written by the owner threads next to the fp32 dgx / dgh the weight GEMMs read, so that A fragments
+//     need no conversion; a tile's 16 rows x 2 planes arrive as 32 bulk copies (cp.async.bulk, one per lane of
+//     warp 0) completing on an mbarrier: no per-thread cp.async issue, no wait_group + CTA barrier;
+//   * row pitch == 4 (mod 32) 32-bit words: the 8 rows x 4 k-pairs of a fragment load hit 32 different banks.
+constexpr int BM_NW = 16;
+constexpr int BM_THREADS = 32 * BM_NW;
+constexpr int BM_NP = 24;                 // units padded to 3 n-tiles of 8
+
+struct RnnBwdTcParams {
+    const float *dy, *whh, *gates, *cells, *y;
+    float *dgx, *dgh;
+    __nv_bfloat16 *xplanes; // [2][B*T][2][GHg] recurrent-side gate gradients as bf16 hi/lo planes (pad columns zero)
+    unsigned *counters;
+    int B, T, H, GHg, pitch, nks;
+    int b_begin, batch_tiles, nslices;
+    long long *trace;
+    int trace_steps;
+};
+
+__device__ __forceinline__ void bm_stamp(const RnnBwdTcParams &p, int s, int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && s < p.trace_steps) p.trace[s * 8 + slot] = clock64();
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int CELL>
+__global__ void __launch_bounds__(BM_THREADS, 1)
+rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
+    constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = p.H, T = p.T, pitch = p.pitch, GHg = p.GHg;
+    const int GH = G * H;
+    __nv_bfloat16 *Wt = reinterpret_cast<__nv_bfloat16 *>(smem_raw);          // [2][BM_NP][pitch]
+    __nv_bfloat16 *dgA = Wt + (size_t)2 * BM_NP * pitch;                       // [2][BW_BT][pitch]
+    float *part = reinterpret_cast<float *>(dgA + (size_t)2 * BW_BT * pitch);  // [BM_NW][BW_BT * BM_NP]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(part + BM_NW * BW_BT * BM_NP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int bid = blockIdx.x;
+    const int slice = bid % p.nslices; bid /= p.nslices;
+    const int bt = bid % p.batch_tiles;
+    const int dir = bid / p.batch_tiles;
+    const int row0 = p.b_begin + bt * BW_BT;
+    const int nrows = min(BW_BT, p.B - row0);
+    const int u0 = slice * BW_HS;
+    unsigned *counter = p.counters + (size_t)(dir * p.batch_tiles + bt) * BW_CTR_STRIDE;
+    const size_t plane_elems = (size_t)p.B * T * 2 * GHg;
+
+    {   // zero both operand arrays (pad rows / columns / absent utterances stay zero), then the resident W planes
+        uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+        const int n16 = (2 * (BM_NP + BW_BT) * pitch * 2) / 16;
+        for (int i = tid; i < n16; i += BM_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const float *wsrc = p.whh + (size_t)dir * GH * H + u0;
+        for (int i = tid; i < GH * BW_HS; i += BM_THREADS) {
+            const int k = i / BW_HS, j = i - k * BW_HS;
+            const float v = __ldg(wsrc + (size_t)k * H + j);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            Wt[(size_t)j * pitch + k] = hi;
+            Wt[(size_t)(BM_NP + j) * pitch + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic zero fill before the bulk copies' writes
+    }
+    __syncthreads();
+
+    // fragment coordinates of mma.m16n8k16: lane = 4*g + t
+    const int fg = lane >> 2, ft = lane & 3;
+    const uint32_t *A32 = reinterpret_cast<const uint32_t *>(dgA);
+    const uint32_t *W32 = reinterpret_cast<const uint32_t *>(Wt);
+    const int pw = pitch >> 1;                                   // row pitch in 32-bit words
+    // owner mapping: thread -> cell (r, j)
+    const bool owner = tid < BW_CELLS;
+    const int orow = tid / BW_HS, oj = tid - orow * BW_HS;
+    const int ob = row0 + orow;
+    const bool oval = owner && ob < p.B;
+    const int ou = u0 + oj;
+    float carry = 0.f;
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? s : (T - 1 - s);
+        const int tp = dir ? t + 1 : t - 1;
+        const int tl = dir ? t - 1 : t + 1;
+        const bool has_prev = (tp >= 0 && tp < T);
+
+        float dyv = 0.f, gv[G], cv = 0.f, pv = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gv[g] = 0.f;
+        const size_t row = ((size_t)ob * T + t) * 2 + dir;
+        if (oval) {
+            dyv = __ldg(p.dy + ((size_t)ob * T + t) * 2 * H + (size_t)dir * H + ou);
+#pragma unroll
+            for (int g = 0; g < G; ++g) gv[g] = __ldg(p.gates + row * GH + (size_t)g * H + ou);
+            cv = __ldg(p.cells + row * H + ou);
+            if (has_prev) {
+                if (CELL == DL4SS_CELL_LSTM) pv = __ldg(p.cells + (((size_t)ob * T + tp) * 2 + dir) * H + ou);
+                else pv = __ldg(p.y + ((size_t)ob * T + tp) * 2 * H + (size_t)dir * H + ou);
+            }
+        }
+
+        float dh = dyv;
+        if (s > 0) {
+            if (warp == 0) {
+                bm_stamp(p, s, 0);
+                if (lane == 0) {
+                    const unsigned want = (unsigned)p.nslices * (unsigned)s;
+                    while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
+                    mbar_expect_tx(bar, (uint32_t)(nrows * 2 * GHg * 2));
+                }
+                bm_stamp(p, s, 1);
+                __syncwarp();
+                asm volatile("fence.proxy.async.global;\n" ::: "memory");   // the siblings' generic stores -> bulk-copy reads
+                const int r = lane >> 1, pl = lane & 1;
+                if (r < nrows)
+                    bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
+                             p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0 + r) * T + tl) * 2 + dir) * GHg,
+                             (uint32_t)(GHg * 2), bar);
+            }
+            mbar_wait(bar, (uint32_t)(s - 1) & 1u);
+            bm_stamp(p, s, 2);
+
+            float acc[3][4];
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+            for (int ks = warp; ks < p.nks; ks += BM_NW) {
+                const int kw = ks * 8 + ft;                          // word index of k = 16*ks + 2*ft
+                uint32_t ah[4], al[4];
+                const uint32_t *a0 = A32 + (size_t)fg * pw + kw;
+                const uint32_t *a1 = a0 + (size_t)BW_BT * pw;        // lo plane
+                ah[0] = a0[0]; ah[1] = a0[8 * pw]; ah[2] = a0[4]; ah[3] = a0[8 * pw + 4];
+                al[0] = a1[0]; al[1] = a1[8 * pw]; al[2] = a1[4]; al[3] = a1[8 * pw + 4];
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const uint32_t *b0 = W32 + (size_t)(8 * n + fg) * pw + kw;
+                    const uint32_t *b1 = b0 + (size_t)BM_NP * pw;    // lo plane
+                    const uint32_t bh0 = b0[0], bh1 = b0[4], bl0 = b1[0], bl1 = b1[4];
+                    mma_bf16_16816(acc[n], ah, bl0, bl1);
+                    mma_bf16_16816(acc[n], al, bh0, bh1);
+                    mma_bf16_16816(acc[n], ah, bh0, bh1);
+                }
+            }
+            float *pwarp = part + (size_t)warp * (BW_BT * BM_NP);
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                *reinterpret_cast<float2 *>(pwarp + fg * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][0], acc[n][1]);
+                *reinterpret_cast<float2 *>(pwarp + (fg + 8) * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][2], acc[n][3]);
+            }
+            bm_stamp(p, s, 3);
+            __syncthreads();
+            bm_stamp(p, s, 4);
+            if (owner) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < BM_NW; ++w) v += part[w * (BW_BT * BM_NP) + orow * BM_NP + oj];
+                dh += v;
+            }
+        }
+
+        if (oval) {
+            float *ox = p.dgx + row * GH + ou;
+            float rec[G];                                       // what the next step's recurrent product consumes
+            if constexpr (CELL == DL4SS_CELL_LSTM) {
+                const float ig = gv[0], fgt = gv[1], gg = gv[2], og = gv[3];
+                const float tc = tanhf(cv);
+                const float dc = fmaf(dh * og, 1.0f - tc * tc, carry);
+                rec[0] = dc * gg * ig * (1.0f - ig);
+                rec[1] = dc * pv * fgt * (1.0f - fgt);
+                rec[2] = dc * ig * (1.0f - gg * gg);
+                rec[3] = dh * tc * og * (1.0f - og);
+                carry = dc * fgt;
+#pragma unroll
+                for (int g = 0; g < G; ++g) __stcg(ox + (size_t)g * H, rec[g]);
+            } else {
+                dh += carry;
+                const float rg = gv[0], zg = gv[1], ng = gv[2];
+                const float hn = cv;
+                const float dn = dh * (1.0f - zg);
+                const float dan = dn * (1.0f - ng * ng);
+                rec[0] = dan * hn * rg * (1.0f - rg);
+                rec[1] = dh * (pv - ng) * zg * (1.0f - zg);
+                rec[2] = dan * rg;
+                carry = dh * zg;
+                float *oh = p.dgh + row * GH + ou;
+                __stcg(ox, rec[0]); __stcg(ox + H, rec[1]); __stcg(ox + 2 * (size_t)H, dan);
+#pragma unroll
+                for (int g = 0; g < G; ++g) __stcg(oh + (size_t)g * H, rec[g]);
+            }
+            __nv_bfloat16 *xh = p.xplanes + row * GHg + ou;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(rec[g]);
+                xh[(size_t)g * H] = hi;
+                xh[plane_elems + (size_t)g * H] = __float2bfloat16_rn(rec[g] - __bfloat162float(hi));
+            }
+        }
+        if (s + 1 < T) {
+            bm_stamp(p, s, 5);
+            __syncthreads();
+            bm_stamp(p, s, 6);
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
+            }
+            bm_stamp(p, s, 7);
+        }
+    }
+}
+
 static long long *g_bwd_trace = nullptr;
 static int g_bwd_trace_steps = 0;
 
@@ -269,6 +499,53 @@ static int launch_rnn_bwd(RnnBwdParams p, int rows_left, cudaStream_t st, int *l
     DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * tiles * p.nslices), dim3(BW_THREADS), args, smem, st));
     count_launch();
     return DL4SS_OK;
+}
+
+static int bwd_tc_ghg(int GH) { return (GH + 7) / 8 * 8; }                // 16-byte rows for the bulk copies
+static int bwd_tc_pitch(int GH) {                                          // bf16 elements; == 4 (mod 32) words
+    int w = cdiv(GH, 16) * 8;
+    w += (4 - w % 32 + 32) % 32;
+    return 2 * w;
+}
+static size_t bwd_tc_smem(int GH) {
+    return (size_t)2 * (BM_NP + BW_BT) * bwd_tc_pitch(GH) * sizeof(__nv_bfloat16) +
+           (size_t)BM_NW * BW_BT * BM_NP * sizeof(float) + 16;
+}
+
+template <int CELL>
+static int launch_rnn_bwd_tc(RnnBwdTcParams p, int rows_left, cudaStream_t st, int *launched_rows) {
+    constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+    const int GH = G * p.H;
+    p.GHg = bwd_tc_ghg(GH);
+    p.pitch = bwd_tc_pitch(GH);
+    p.nks = cdiv(GH, 16);
+    p.nslices = p.H / BW_HS;
+    const size_t smem = bwd_tc_smem(GH);
+    auto kern = rnn_bwd_tc_kernel<CELL>;
+    DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DL4SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BM_THREADS, smem));
+    const int max_tiles = per_sm * sm_count() / (2 * p.nslices);
+    if (max_tiles < 1) {
+        set_error("rnn_layer_bwd_tc: %d co-resident CTAs cannot hold one tile (%d slices x 2 directions)",
+                  per_sm * sm_count(), p.nslices);
+        return DL4SS_EUNSUPPORTED;
+    }
+    int tiles = cdiv(rows_left, BW_BT);
+    if (tiles > max_tiles) tiles = max_tiles;
+    p.batch_tiles = tiles;
+    *launched_rows = tiles * BW_BT;
+    void *args[] = {(void *)&p};
+    DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * tiles * p.nslices), dim3(BM_THREADS), args, smem, st));
+    count_launch();
+    return DL4SS_OK;
+}
+
+static bool rnn_bwd_tc_supported(int H, int cell) {
+    if (!(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU)) return false;
+    if (H < BW_HS || H % BW_HS != 0) return false;
+    const int G = (cell == DL4SS_CELL_LSTM) ? 4 : 3;
+    return bwd_tc_smem(G * H) <= 227 * 1024;
 }
 
 static bool rnn_bwd_supported(int H, int cell) {
@@ -332,6 +609,56 @@ extern "C" int dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, 
         int done = 0;
         int rc = (cell == DL4SS_CELL_LSTM) ? launch_rnn_bwd<DL4SS_CELL_LSTM>(p, B - b0, st, &done)
                                            : launch_rnn_bwd<DL4SS_CELL_GRU>(p, B - b0, st, &done);
+        if (rc) return rc;
+        ctr += (size_t)2 * (done / BW_BT) * BW_CTR_STRIDE;
+        b0 += done;
+    }
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_rnn_bwd_tc_supported(int H, int cell) { return rnn_bwd_tc_supported(H, cell) ? 1 : 0; }
+
+extern "C" size_t dl4ss_rnn_bwd_tc_xplanes_bytes(int B, int T, int H, int cell) {
+    if (B <= 0 || T <= 0 || H <= 0) return 0;
+    const int G = (cell == DL4SS_CELL_LSTM) ? 4 : 3;
+    return (size_t)2 * B * T * 2 * bwd_tc_ghg(G * H) * sizeof(__nv_bfloat16);
+}
+
+extern "C" int dl4ss_rnn_layer_bwd_tc(int cell, const float *dy, const float *whh, const float *gates_save,
+                                      const float *cell_save, const float *y, float *dgx, float *dgh, void *xplanes,
+                                      int B, int T, int H, void *workspace, size_t workspace_bytes, void *stream) {
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_bwd_tc: bad cell %d", cell);
+    DL4SS_CHECK_ARG(dy && whh && gates_save && cell_save && dgx && xplanes, "rnn_layer_bwd_tc: null operand");
+    DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || (y && dgh), "rnn_layer_bwd_tc: GRU needs y and dgh");
+    DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1, "rnn_layer_bwd_tc: bad B/T/H %d/%d/%d", B, T, H);
+    if (!rnn_bwd_tc_supported(H, cell)) {
+        set_error("rnn_layer_bwd_tc: H=%d unsupported (needs a multiple of %d whose W_hh slice fits shared memory); "
+                  "use dl4ss_rnn_bwd_step", H, BW_HS);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0) return DL4SS_OK;
+    const size_t need = dl4ss_rnn_bwd_workspace_bytes(B, T, H, cell);
+    if (!workspace || workspace_bytes < need) {
+        set_error("rnn_layer_bwd_tc: workspace %zu B < %zu B", workspace_bytes, need);
+        return DL4SS_EWORKSPACE;
+    }
+    DL4SS_CHECK_ARG((((uintptr_t)workspace) & 255) == 0, "rnn_layer_bwd_tc: workspace must be 256-byte aligned");
+    DL4SS_CHECK_ARG((((uintptr_t)xplanes) & 15) == 0, "rnn_layer_bwd_tc: xplanes must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    DL4SS_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    RnnBwdTcParams p;
+    p.dy = dy; p.whh = whh; p.gates = gates_save; p.cells = cell_save; p.y = y; p.dgx = dgx; p.dgh = dgh;
+    p.xplanes = (__nv_bfloat16 *)xplanes;
+    p.B = B; p.T = T; p.H = H; p.GHg = p.pitch = p.nks = 0; p.batch_tiles = 0; p.nslices = 0;
+    p.trace = g_bwd_trace; p.trace_steps = g_bwd_trace_steps;
+    unsigned *ctr = (unsigned *)workspace;
+    int b0 = 0;
+    while (b0 < B) {
+        p.b_begin = b0;
+        p.counters = ctr;
+        int done = 0;
+        int rc = (cell == DL4SS_CELL_LSTM) ? launch_rnn_bwd_tc<DL4SS_CELL_LSTM>(p, B - b0, st, &done)
+                                           : launch_rnn_bwd_tc<DL4SS_CELL_GRU>(p, B - b0, st, &done);
         if (rc) return rc;
         ctr += (size_t)2 * (done / BW_BT) * BW_CTR_STRIDE;
         b0 += done;

@@ -258,6 +258,18 @@ class TrainStep(object):
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, device=dy.device, dtype=torch.uint8)
             st['bwd_ws'] = ws
+        if M.use_tensor_cores() and lib.dl4ss_rnn_bwd_tc_supported(H, cell) != 0:
+            xb = lib.dl4ss_rnn_bwd_tc_xplanes_bytes(B, T, H, cell)
+            xp = st.get('xplanes')
+            if xp is None or xp.numel() != xb:
+                xp = torch.zeros(xb, device=dy.device, dtype=torch.uint8)      # pad columns stay zero for good
+                st['xplanes'] = xp
+            rc = lib.dl4ss_rnn_layer_bwd_tc(cell, _lib.ptr(dy), _lib.ptr(whh), _lib.ptr(st['gates']),
+                                            _lib.ptr(st['cells']), _lib.ptr(st['y']), _lib.ptr(st['dgx']),
+                                            _lib.ptr(st['dgh']), ctypes.c_void_p(xp.data_ptr()), B, T, H,
+                                            ctypes.c_void_p(ws.data_ptr()), need, _lib.stream())
+            _lib.check(rc, 'dl4ss_rnn_layer_bwd_tc')
+            return
         rc = lib.dl4ss_rnn_layer_bwd(cell, _lib.ptr(dy), _lib.ptr(whh), _lib.ptr(st['gates']), _lib.ptr(st['cells']),
                                      _lib.ptr(st['y']), _lib.ptr(st['dgx']), _lib.ptr(st['dgh']), B, T, H,
                                      ctypes.c_void_p(ws.data_ptr()), need, _lib.stream())

@@ -252,6 +252,16 @@ size_t dl4ss_rnn_bwd_workspace_bytes(int B, int T, int H, int cell);
 int    dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, const float *gates_save,
                            const float *cell_save, const float *y, float *dgx, float *dgh, int B, int T, int H,
                            void *workspace, size_t workspace_bytes, void *stream);
+/* Tensor-core form (bf16x3 on warp-level mma.sync.m16n8k16, fp32 accumulation): the per-step product has K = G*H
+ * against a 16 x 20 output, which suits many warps issuing small MMAs, not tcgen05's single-thread 128-row UMMAs.
+ * Same contract plus `xplanes`: caller-owned bf16 [2 (hi,lo)][B*T][2][GHg] (GHg = G*H rounded up to 8,
+ * dl4ss_rnn_bwd_tc_xplanes_bytes() bytes, 16-byte aligned) through which the CTAs exchange the recurrent-side gate
+ * gradients; the caller zero-fills it ONCE (the kernel never writes the GHg - G*H pad columns, which must be zero). */
+int    dl4ss_rnn_bwd_tc_supported(int H, int cell);
+size_t dl4ss_rnn_bwd_tc_xplanes_bytes(int B, int T, int H, int cell);
+int    dl4ss_rnn_layer_bwd_tc(int cell, const float *dy, const float *whh, const float *gates_save,
+                              const float *cell_save, const float *y, float *dgx, float *dgh, void *xplanes,
+                              int B, int T, int H, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

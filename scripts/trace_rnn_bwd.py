@@ -25,7 +25,17 @@ need = lib.dl4ss_rnn_bwd_workspace_bytes(B, T, H, c)
 ws = torch.empty(need, device=dev, dtype=torch.uint8)
 
 
+TC = (sys.argv[3] if len(sys.argv) > 3 else 'tc') == 'tc'
+xp = torch.zeros(lib.dl4ss_rnn_bwd_tc_xplanes_bytes(B, T, H, c), device=dev, dtype=torch.uint8)
+
+
 def run():
+    if TC:
+        rc = lib.dl4ss_rnn_layer_bwd_tc(c, L.ptr(dy), L.ptr(whh), L.ptr(gates), L.ptr(cells), L.ptr(y), L.ptr(dgx),
+                                        L.ptr(dgh), ctypes.c_void_p(xp.data_ptr()), B, T, H,
+                                        ctypes.c_void_p(ws.data_ptr()), need, L.stream())
+        L.check(rc, 'dl4ss_rnn_layer_bwd_tc')
+        return
     rc = lib.dl4ss_rnn_layer_bwd(c, L.ptr(dy), L.ptr(whh), L.ptr(gates), L.ptr(cells), L.ptr(y), L.ptr(dgx), L.ptr(dgh),
                                  B, T, H, ctypes.c_void_p(ws.data_ptr()), need, L.stream())
     L.check(rc, 'dl4ss_rnn_layer_bwd')
@@ -39,7 +49,7 @@ for _ in range(5):
     run()
 e1.record()
 torch.cuda.synchronize()
-print('B=%d %s: %.3f ms per layer launch' % (B, CELL, e0.elapsed_time(e1) / 5))
+print('B=%d %s %s: %.3f ms per layer launch' % (B, CELL, 'tc' if TC else 'fp32', e0.elapsed_time(e1) / 5))
 steps = 64
 buf = torch.zeros(steps * 8, dtype=torch.int64, device=dev)
 lib.dl4ss_rnn_bwd_set_trace(ctypes.c_void_p(buf.data_ptr()), steps)
