@@ -419,6 +419,9 @@ def run_train(args):
         cfg = workload_config(B)
         cfg['workload'] = 'TDAA_beta 2-speaker training step (BASELINE configs[3]): STFT -> BLSTM attention masks -> MSE loss -> backward -> gradient all-reduce -> Adam'
         cfg['allreduce_bytes_per_step'] = nparams * 4 if world > 1 else 0
+        cfg['l2'] = 'working set >> 126 MB L2 (saved gates 192 MB/layer at 64 utterances)'
+        cfg['launch'] = ('eager launches; the BPTT chain of each layer is one persistent kernel (dl4ss_rnn_layer_bwd_tc), '
+                         'the forward recurrence one persistent kernel per layer (dl4ss_rnn_layer_tc_fwd)')
         print(json.dumps({'metric': 'training_audio_seconds_per_second', 'value': audio_s / (ms * 1e-3), 'unit': 'audio-s/s',
                           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
                           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',

@@ -415,9 +415,12 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
             }
         }
 
+        // gate arithmetic; the bf16 planes the siblings wait for are published first, the fp32 arrays the weight GEMMs
+        // read follow after the release, off the chain
+        float rec[G], dxn = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) rec[g] = 0.f;
         if (oval) {
-            float *ox = p.dgx + row * GH + ou;
-            float rec[G];                                       // what the next step's recurrent product consumes
             if constexpr (CELL == DL4SS_CELL_LSTM) {
                 const float ig = gv[0], fgt = gv[1], gg = gv[2], og = gv[3];
                 const float tc = tanhf(cv);
@@ -427,22 +430,16 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
                 rec[2] = dc * ig * (1.0f - gg * gg);
                 rec[3] = dh * tc * og * (1.0f - og);
                 carry = dc * fgt;
-#pragma unroll
-                for (int g = 0; g < G; ++g) __stcg(ox + (size_t)g * H, rec[g]);
             } else {
                 dh += carry;
                 const float rg = gv[0], zg = gv[1], ng = gv[2];
                 const float hn = cv;
                 const float dn = dh * (1.0f - zg);
-                const float dan = dn * (1.0f - ng * ng);
-                rec[0] = dan * hn * rg * (1.0f - rg);
+                dxn = dn * (1.0f - ng * ng);
+                rec[0] = dxn * hn * rg * (1.0f - rg);
                 rec[1] = dh * (pv - ng) * zg * (1.0f - zg);
-                rec[2] = dan * rg;
+                rec[2] = dxn * rg;
                 carry = dh * zg;
-                float *oh = p.dgh + row * GH + ou;
-                __stcg(ox, rec[0]); __stcg(ox + H, rec[1]); __stcg(ox + 2 * (size_t)H, dan);
-#pragma unroll
-                for (int g = 0; g < G; ++g) __stcg(oh + (size_t)g * H, rec[g]);
             }
             __nv_bfloat16 *xh = p.xplanes + row * GHg + ou;
 #pragma unroll
@@ -461,6 +458,18 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
             }
             bm_stamp(p, s, 7);
+        }
+        if (oval) {
+            float *ox = p.dgx + row * GH + ou;
+            if constexpr (CELL == DL4SS_CELL_LSTM) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) __stcs(ox + (size_t)g * H, rec[g]);
+            } else {
+                float *oh = p.dgh + row * GH + ou;
+                __stcs(ox, rec[0]); __stcs(ox + H, rec[1]); __stcs(ox + 2 * (size_t)H, dxn);
+#pragma unroll
+                for (int g = 0; g < G; ++g) __stcs(oh + (size_t)g * H, rec[g]);
+            }
         }
     }
 }
