@@ -29,6 +29,9 @@ SIGNATURES = {
     'dl4ss_linear_fwd': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     'dl4ss_rnn_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'dl4ss_rnn_layer_fwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    'dl4ss_rnn_mma_supported': (c_i, [c_i, c_i]),
+    'dl4ss_rnn_mma_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
+    'dl4ss_rnn_layer_mma_fwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     'dl4ss_rnn_tc_supported': (c_i, [c_i, c_i]),
     'dl4ss_rnn_tc_set_trace': (None, [c_p, c_i]),
     'dl4ss_rnn_tc_whh_bytes': (c_sz, [c_i]),

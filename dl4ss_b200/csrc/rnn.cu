@@ -320,6 +320,8 @@ static int rnn_dispatch(RnnParams p, int rows_left, cudaStream_t st, int *launch
     int rc = DL4SS_EUNSUPPORTED;
     if (rows_left > 32) rc = launch_rnn<CELL, 10, 2, 2, 32>(p, rows_left, st, launched_rows);
     if (rc == DL4SS_EUNSUPPORTED && rows_left > 8) rc = launch_rnn<CELL, 10, 2, 1, 32>(p, rows_left, st, launched_rows);
+    // H = 600: a 10-unit slice (96 KB of W_hh) next to a 32-utterance h tile (77 KB) still fits; one unit per warp
+    if (rc == DL4SS_EUNSUPPORTED && rows_left > 8) rc = launch_rnn<CELL, 10, 1, 1, 32>(p, rows_left, st, launched_rows);
     if (rc == DL4SS_EUNSUPPORTED) rc = launch_rnn<CELL, 5, 2, 1, 8>(p, rows_left, st, launched_rows);
     return rc;
 }

@@ -169,9 +169,19 @@ def use_tc_recurrence(H, cell):
             and bool(_lib.load().dl4ss_rnn_tc_supported(H, cell)))
 
 
+def use_mma_recurrence(H, cell):
+    """Warp-level tensor-core recurrent kernel (bf16x3 mma.sync) for hidden sizes the tcgen05 form cannot hold (H = 600)."""
+    return (use_tensor_cores() and config.RNN_TENSOR_CORES and not use_tc_recurrence(H, cell)
+            and bool(_lib.load().dl4ss_rnn_mma_supported(H, cell)))
+
+
 def recurrent_workspace(B, T, H, cell, tc_rec, device):
+    """tc_rec: True (tcgen05 kernel), 'mma' (warp-level tensor-core kernel) or False (fp32 kernel)."""
     lib = _lib.load()
-    n = int(lib.dl4ss_rnn_tc_workspace_bytes(B, T, H, cell) if tc_rec else lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
+    if tc_rec == 'mma':
+        n = int(lib.dl4ss_rnn_mma_workspace_bytes(B, T, H, cell))
+    else:
+        n = int(lib.dl4ss_rnn_tc_workspace_bytes(B, T, H, cell) if tc_rec else lib.dl4ss_rnn_workspace_bytes(B, T, H, cell))
     return torch.empty(n, device=device, dtype=torch.uint8)
 
 
@@ -193,7 +203,12 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     lib = _lib.load()
     if y is None:
         y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
-    if tc_rec:
+    if tc_rec == 'mma':
+        rc = lib.dl4ss_rnn_layer_mma_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
+                                         _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
+                                         _lib.ptr(ws, torch.uint8), ws.numel(), _lib.stream())
+        _lib.check(rc, 'dl4ss_rnn_layer_mma_fwd')
+    elif tc_rec:
         rc = lib.dl4ss_rnn_layer_tc_fwd(cell, _lib.ptr(xproj), _lib.ptr(whh_planes(lw, cell, H), torch.bfloat16),
                                         _lib.ptr(lw['bhn']), _lib.ptr(y), B, T, H, _lib.ptr(gates), _lib.ptr(cells),
                                         _lib.ptr(y_planes, torch.bfloat16), _lib.ptr(hmean),
@@ -222,11 +237,13 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None):
     B, T, _ = x.shape
     dev = x.device
     tc_rec = use_tc_recurrence(H, cell)
+    if not tc_rec and use_mma_recurrence(H, cell):
+        tc_rec = 'mma'
     ws = recurrent_workspace(B, T, H, cell, tc_rec, dev)
     inp = x.contiguous()
     xproj = torch.empty(B * T, 2 * G * H, device=dev, dtype=torch.float32)
     layers = packed.get()
-    fuse = tc_rec and use_tensor_cores()        # K3 emits its output pre-split for the next projection (+ the T-mean)
+    fuse = tc_rec is True and use_tensor_cores()        # K3 emits its output pre-split for the next projection (+ the T-mean)
     planes = None                               # bf16 hi/lo planes of `inp`, when the producer made them
     hmean = None
     Kpy = (2 * H + 63) // 64 * 64

@@ -102,6 +102,19 @@ int dl4ss_rnn_layer_fwd(int cell, const float *xproj, const float *whh, const fl
                         float *y, int B, int T, int H, float *gates_save, float *cell_save,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- K3 on warp-level tensor cores for large hidden sizes (bf16x3 mma.sync.m16n8k16) ---------------------
+ * Same contract as dl4ss_rnn_layer_fwd.  For hidden sizes the TMEM-resident tcgen05 form cannot hold -- the speaker
+ * classifier's BLSTM 3x600 (MIX_SPEECH_classifier, TDAA_beta/main_run_sstune_EvalVer.py:305-326): W_hh resident ONCE
+ * on the chip (a CTA owns a direction and 10 hidden units and walks every 16-utterance tile of the batch each step).
+ * Supported when dl4ss_rnn_mma_supported(H, cell) != 0 (H a multiple of 10, 2*H/10 <= number of SMs, slice fits
+ * shared memory: H <= 740 on B200).  workspace: dl4ss_rnn_mma_workspace_bytes() bytes, 256-byte aligned, zero-filled
+ * by the callee (release counters + the L2-resident bf16 exchange buffer). */
+int    dl4ss_rnn_mma_supported(int H, int cell);
+size_t dl4ss_rnn_mma_workspace_bytes(int B, int T, int H, int cell);
+int    dl4ss_rnn_layer_mma_fwd(int cell, const float *xproj, const float *whh, const float *bhn,
+                               float *y, int B, int T, int H, float *gates_save, float *cell_save,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- K3 on the tensor cores (tcgen05, bf16x3 split of h and W_hh, fp32 TMEM accumulation) -----------
  * Same contract as dl4ss_rnn_layer_fwd except that W_hh arrives pre-packed by dl4ss_rnn_tc_pack_whh:
  * whh [2,G*H,H] fp32 -> bf16 hi/lo planes [2][2 dir * 4H rows][Kp], row dir*4H + 4*u + g = gate g of

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0,'.')
 import torch, dl4ss_b200 as d
 d.config.HIDDEN_UNITS=300
-for B in (16, 64):
+for B in (16, 64, 256):
     cls = d.MIX_SPEECH_classifier(129, 313, 101).cuda()
     x = torch.rand(B, 313, 129, device='cuda')
     with torch.no_grad():

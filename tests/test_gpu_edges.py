@@ -186,3 +186,48 @@ def test_recursive_extract_matches_oracle(cuda):
     assert (got.cpu() - want).abs().max().item() < 1e-4 * 2.0
     resid = feas.cuda().unsqueeze(1) - got.cumsum(1)
     assert (resid[:, -1].abs().sum() < resid[:, 0].abs().sum()).item()
+
+
+@pytest.mark.parametrize('cell,B,T,H', [('lstm', 5, 7, 600), ('gru', 37, 6, 600), ('lstm', 70, 5, 300), ('gru', 3, 9, 40),
+                                         ('lstm', 16, 1, 600)])
+def test_rnn_mma_layer_equals_fp32_layer(cuda, cell, B, T, H):
+    """dl4ss_rnn_layer_mma_fwd (warp-level tensor cores, bf16x3; the H = 600 classifier path) against the fp32
+    recurrent kernel on the same hoisted projection: outputs, saved gates and cells; partial and multiple tiles."""
+    import ctypes
+    from dl4ss_b200 import _lib as L
+    lib = L.load()
+    G = 4 if cell == 'lstm' else 3
+    c = L.CELL_LSTM if cell == 'lstm' else L.CELL_GRU
+    assert lib.dl4ss_rnn_mma_supported(H, c) == 1
+    g = torch.Generator().manual_seed(B * 131 + H)
+    xproj = torch.randn(B, T, 2, G * H, generator=g).to(cuda)
+    whh = (torch.randn(2, G * H, H, generator=g) / H ** 0.5).to(cuda)
+    bhn = torch.randn(2, H, generator=g).to(cuda) if G == 3 else None
+
+    def run(fn, wsb):
+        y = torch.full((B, T, 2 * H), float('nan'), device=cuda)
+        gates = torch.full((B, T, 2, G * H), float('nan'), device=cuda)
+        cells = torch.full((B, T, 2, H), float('nan'), device=cuda)
+        need = wsb(B, T, H, c)
+        ws = torch.empty(need, device=cuda, dtype=torch.uint8)
+        rc = fn(c, L.ptr(xproj), L.ptr(whh), L.ptr(bhn), L.ptr(y), B, T, H, L.ptr(gates), L.ptr(cells),
+                ctypes.c_void_p(ws.data_ptr()), need, L.stream())
+        L.check(rc, 'rnn layer')
+        torch.cuda.synchronize()
+        return y, gates, cells
+
+    y0, g0, c0 = run(lib.dl4ss_rnn_layer_fwd, lib.dl4ss_rnn_workspace_bytes)
+    y1, g1, c1 = run(lib.dl4ss_rnn_layer_mma_fwd, lib.dl4ss_rnn_mma_workspace_bytes)
+    assert (y1 - y0).abs().max().item() < 2e-5
+    assert (g1 - g0).abs().max().item() < 2e-5
+    assert (c1 - c0).abs().max().item() < 2e-5 * max(1.0, c0.abs().max().item())
+
+
+def test_rnn_mma_unsupported_is_loud(cuda):
+    from dl4ss_b200 import _lib as L
+    lib = L.load()
+    assert lib.dl4ss_rnn_mma_supported(601, L.CELL_LSTM) == 0
+    assert lib.dl4ss_rnn_mma_supported(1000, L.CELL_LSTM) == 0
+    x = torch.zeros(16, device=cuda)
+    rc = lib.dl4ss_rnn_layer_mma_fwd(L.CELL_LSTM, L.ptr(x), L.ptr(x), None, L.ptr(x), 1, 1, 601, None, None, None, 0, L.stream())
+    assert rc != 0 and b'unsupported' in lib.dl4ss_last_error()
