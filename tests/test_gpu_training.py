@@ -20,7 +20,10 @@ def _grads(mods):
 
 
 @pytest.mark.parametrize('cell,layers,cplx,S,B,T', [('lstm', 2, False, 2, 3, 19), ('gru', 2, True, 3, 2, 14),
-                                                     ('lstm', 1, False, 2, 2, 7), ('gru', 1, False, 2, 4, 11)])
+                                                     ('lstm', 1, False, 2, 2, 7), ('gru', 1, False, 2, 4, 11),
+                                                     # BASELINE configs[3] depth and length: 4 layers, the full 313-step chain,
+                                                     # more utterances than one 16-row tile
+                                                     ('lstm', 4, False, 2, 18, 313)])
 def test_gradients_match_autograd(cuda, cell, layers, cplx, S, B, T):
     import dl4ss_b200 as d
     from oracle import modules_ref as mr
