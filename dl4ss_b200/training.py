@@ -320,21 +320,43 @@ class TrainStep(object):
             dgx, dgh = st['dgx'], st['dgh']
             x2d = sv['x'].reshape(B * T, -1)
             dgx2d = dgx.view(B * T, 2 * G * H)
-            dW_ih = _mm_tn(dgx2d, x2d)                                           # [2*G*H, in]
-            db_x = dgx2d.sum(0)
-            dgr = dgh if gru else dgx                                            # recurrent-side gate grads
             y = sv['y']
-            for d, suf in enumerate(('', '_reverse')):
-                sl = slice(d * G * H, (d + 1) * G * H)
-                _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
-                _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
-                if d == 0:       # h_{t-1} of the forward direction is y[:, t-1, :H]
-                    dg_t, h_prev = dgr[:, 1:, 0, :], y[:, :-1, :H]
-                else:            # the reverse direction came from t+1
-                    dg_t, h_prev = dgr[:, :-1, 1, :], y[:, 1:, H:]
-                _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)),
-                       _mm_tn(dg_t.reshape(-1, G * H), h_prev.reshape(-1, H)))
-                _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
+            db_x = dgx2d.sum(0)
+            if not gru and M.use_tensor_cores() and config.TRAIN_TC_GEMMS:
+                # LSTM: the recurrent-side gate gradients ARE dgx, so one transposed split of dgx serves dW_ih and both
+                # directions' dW_hh: the latter come out of ONE product against the time-shifted layer output
+                # (columns [0,H): y[t-1] of the forward direction, [H,2H): y[t+1] of the reverse one; the rows without
+                # a predecessor stay zero) as the two diagonal blocks.
+                R = B * T
+                dg_t_planes = M.split_bf16_t(dgx2d)
+                dW_ih = M.linear_tc(dg_t_planes, M.split_bf16_t(x2d), None, 2 * G * H, x2d.shape[1], R, split_k=True)
+                ysh = st.get('ysh')
+                if ysh is None or ysh.shape != y.shape:
+                    ysh = torch.zeros_like(y)
+                    st['ysh'] = ysh
+                ysh[:, 1:, :H].copy_(y[:, :-1, :H])
+                ysh[:, :-1, H:].copy_(y[:, 1:, H:])
+                P = M.linear_tc(dg_t_planes, M.split_bf16_t(ysh.view(R, 2 * H)), None, 2 * G * H, 2 * H, R, split_k=True)
+                for d, suf in enumerate(('', '_reverse')):
+                    sl = slice(d * G * H, (d + 1) * G * H)
+                    _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
+                    _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
+                    _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)), P[sl, d * H:(d + 1) * H])
+                    _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), db_x[sl])
+            else:
+                dW_ih = _mm_tn(dgx2d, x2d)                                       # [2*G*H, in]
+                dgr = dgh if gru else dgx                                        # recurrent-side gate grads
+                for d, suf in enumerate(('', '_reverse')):
+                    sl = slice(d * G * H, (d + 1) * G * H)
+                    _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
+                    _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
+                    if d == 0:       # h_{t-1} of the forward direction is y[:, t-1, :H]
+                        dg_t, h_prev = dgr[:, 1:, 0, :], y[:, :-1, :H]
+                    else:            # the reverse direction came from t+1
+                        dg_t, h_prev = dgr[:, :-1, 1, :], y[:, 1:, H:]
+                    _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)),
+                           _mm_tn(dg_t.reshape(-1, G * H), h_prev.reshape(-1, H)))
+                    _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
             if l > 0:
                 dy = _mm_nn(dgx2d, lw['wih']).view(B, T, -1).contiguous()
 
