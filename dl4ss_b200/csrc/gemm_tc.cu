@@ -88,12 +88,13 @@ split_bf16_t_kernel(const float *__restrict__ x, long long ld, int R, int C, int
 }
 
 // ------------------------------------------------------------------------------------------ epilogues
-template <int ACT>          // DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID, compile time: the epilogue is on the critical path
+// ACT: DL4SS_ACT_NONE | DL4SS_ACT_TANH | DL4SS_ACT_SIGMOID; ATOMIC: split-K launch, partial tiles are summed into a zeroed C
+// with red.add (ACT must be NONE).  Both compile time: the epilogue is on the critical path.
+template <int ACT, bool ATOMIC = false>
 struct EpiPlain {
     float *C;
     const float *bias;
     int ldc;
-    int atomic;          // split-K launch: partial tiles are summed into a zeroed C with red.add (ACT must be NONE)
 };
 struct EpiAttn {
     const float *bias;   // [F*E]
@@ -110,7 +111,7 @@ constexpr int ATT_SMAX = 4;                     // speakers per utterance handle
 template <typename Epi> struct EpiTraits;
 // PARTS: epilogue warps per TMEM sub-partition (each takes 1/PARTS of the tile's columns).  The plain store
 // epilogue is bound by its row-strided stores and is fastest with 2, the attention epilogue is math bound: 4.
-template <int ACT> struct EpiTraits<EpiPlain<ACT>> { static constexpr int NSTEP = TBN; static constexpr int PARTS = 2; };
+template <int ACT, bool ATOMIC> struct EpiTraits<EpiPlain<ACT, ATOMIC>> { static constexpr int NSTEP = TBN; static constexpr int PARTS = 2; };
 template <> struct EpiTraits<EpiAttn> { static constexpr int NSTEP = ATT_BINS * ATT_E; static constexpr int PARTS = ATT_BINS; };
 
 __device__ __forceinline__ float crm_value_tc(float energy, float crm_k, float crm_c) {
@@ -129,10 +130,10 @@ __device__ __forceinline__ float apply_act(float x) {
 // TMEM hands every lane ONE ROW; written out like that a store instruction touches 32 different lines with
 // 16 bytes each.  The 32x32 block is transposed through a per-warp smem tile instead, so that 8 lanes write
 // one row's 128 contiguous bytes (4 full lines per instruction); bias and activation ride the transposed side.
-template <int ACT>
-__device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT> &e, uint32_t taddr, int m_base, int n0, int M, int N,
+template <int ACT, bool ATOMIC>
+__device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT, ATOMIC> &e, uint32_t taddr, int m_base, int n0, int M, int N,
                                               int part, int lane, float *stage) {
-    constexpr int CH = TBN / 32 / EpiTraits<EpiPlain<ACT>>::PARTS;
+    constexpr int CH = TBN / 32 / EpiTraits<EpiPlain<ACT, ATOMIC>>::PARTS;
     const bool vec = ((e.ldc & 3) == 0) && ((((uintptr_t)e.C) & 15) == 0);
     const int rsub = lane >> 3, col = (lane & 7) * 4;
 #pragma unroll 1
@@ -160,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT> &e, uint32_t t
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = apply_act<ACT>(stage[row * TC_STAGE_PITCH + col + k] + bz[k]);
             float *dst = e.C + (size_t)m * e.ldc + n + col;
-            if (e.atomic) {
+            if (ATOMIC) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (n + col + k < N) atomicAdd(dst + k, o[k]);
             } else if (vec && n + col + 3 < N) {
@@ -233,8 +234,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiAttn &e, uint32_t taddr, 
 
 // the epilogue a K split of a tile runs: only split 0 adds the bias
 template <int ACT>
-__device__ __forceinline__ EpiPlain<ACT> epi_of_split(const EpiPlain<ACT> &e, int ks) {
-    EpiPlain<ACT> r = e;
+__device__ __forceinline__ const EpiPlain<ACT, false> &epi_of_split(const EpiPlain<ACT, false> &e, int) { return e; }
+template <int ACT>
+__device__ __forceinline__ EpiPlain<ACT, true> epi_of_split(const EpiPlain<ACT, true> &e, int ks) {
+    EpiPlain<ACT, true> r = e;
     if (ks != 0) r.bias = nullptr;
     return r;
 }
@@ -279,7 +282,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int tile = w / nsplit, ks = w - tile * nsplit;
+                const int tile = (nsplit == 1) ? w : w / nsplit, ks = w - tile * nsplit;
                 const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
                 const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -299,7 +302,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int ks = w % nsplit;
+                const int ks = (nsplit == 1) ? 0 : w % nsplit;
                 const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -331,7 +334,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                        (size_t)((part * 4 + quarter) % TC_STORE_WARPS) * 32 * TC_STAGE_PITCH;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int tile = w / nsplit, ks = w - tile * nsplit;
+            const int tile = (nsplit == 1) ? w : w / nsplit, ks = w - tile * nsplit;
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -480,7 +483,8 @@ extern "C" int dl4ss_linear_tc_splitk_fwd(const void *a_planes, const void *w_pl
     const int n_tiles = cdiv(N, TBN);
     const int ns = pick_ksplit((long long)cdiv(M, TBM) * n_tiles, cdiv(K, TBK), sm_count());
     if (ns > 1) DL4SS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
-    return launch_tc(a_planes, w_planes, M, N, K, n_tiles, EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc, ns > 1 ? 1 : 0}, st, ns);
+    if (ns > 1) return launch_tc(a_planes, w_planes, M, N, K, n_tiles, EpiPlain<DL4SS_ACT_NONE, true>{C, bias, ldc}, st, ns);
+    return launch_tc(a_planes, w_planes, M, N, K, n_tiles, EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, st, 1);
 }
 
 extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
