@@ -433,6 +433,44 @@ def run_train(args):
     return 0
 
 
+def training_extra(device, B=64, steps=5, warmup=3):
+    """BASELINE configs[3] on this GPU, reported next to the headline line (single-GPU runs only): the training step of
+    run_train() (STFTs -> forward with saved gates -> loss -> backward -> Adam) at B utterances, CUDA-event timed."""
+    import dl4ss_b200 as d
+    W = WORKLOAD
+    sep = build_model(device)
+    step = d.TrainStep(sep.mix, sep.emb, sep.att, sep.adj)
+    opt = torch.optim.Adam([{'params': step.parameters()}], lr=2e-4)
+    g = torch.Generator(device=device).manual_seed(11)
+    src = torch.randn(B, W['S'], W['L'], device=device, generator=g)
+    src = src / src.abs().amax(2, keepdim=True)
+    wav = src.sum(1).contiguous()
+    gi = torch.Generator().manual_seed(7)
+    idx = torch.sort(torch.stack([torch.randperm(W['num_spk'], generator=gi)[:W['S']] for _ in range(B)]), 1)[0].to(device)
+
+    def one_step():
+        batch = d.prepare_batch(wav, W['n_fft'], W['hop'], False, sources=src)
+        return step.step(opt, batch['mix_feas'], idx, batch['multi_spk_fea'].contiguous(), global_batch=B)
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    n0 = d.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one_step()[0]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {'workload': 'training step (BASELINE configs[3]): STFT -> BLSTM attention masks -> MSE loss -> backward -> Adam',
+           'batch_per_gpu': B, 'ms_per_step': ms, 'value': B * W['L'] / SR / (ms * 1e-3), 'unit': 'audio-s/s',
+           'steps': steps, 'warmup': warmup, 'gpu_launches_per_step': (d.launch_count() - n0) // steps, 'loss': float(loss)}
+    del step, opt, sep, src, wav
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(B):
     W = WORKLOAD
     return {'workload': W['name'], 'batch_per_gpu': B, 'utterance_s': W['L'] / SR, 'sample_rate': SR,
@@ -454,6 +492,7 @@ def main():
     ap.add_argument('--cpu-baseline-utts', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1: replay the step from one CUDA graph (default); 0: eager launches')
+    ap.add_argument('--no-train-extra', action='store_true', help='skip the configs[3] training-step timing added to the line at N=1')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="'train': BASELINE configs[3], STFT -> encoder -> masks -> loss -> backward -> all-reduce -> Adam")
     ap.add_argument('--train-batch', type=int, default=64, help='utterances per GPU per training step')
@@ -598,6 +637,12 @@ def main():
             dt = time.perf_counter() - t0
             cpu = {'value': n_utt * W['L'] / SR * reps / dt, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
                    'sample': '%d reps of %d utterances x 5 s (same model/config, bounded sample)' % (reps, n_utt)}
+        train = None
+        if world == 1 and not args.no_train_extra:
+            try:
+                train = training_extra(device)
+            except Exception as e:       # the headline line must not depend on the extra measurement
+                train = {'error': repr(e)[:200]}
         bytes_in = B * W['L'] * 4 + idx.numel() * 8
         bytes_out = B * W['S'] * Lout * 4
         line = {'metric': 'separated_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s',
@@ -607,7 +652,7 @@ def main():
                 'e2e': {'value': e2e_v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': bytes_in,
                         'd2h_bytes_per_step': bytes_out, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_stages': stages,
-                'cpu_baseline': cpu}
+                'cpu_baseline': cpu, 'configs3_training': train}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

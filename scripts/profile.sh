@@ -1,7 +1,7 @@
 # usage (on the GPU box via gpurun): TAG=r1b bash scripts/profile.sh
 set -x
 TAG=${TAG:-r1}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train-extra"
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 $CMD > gpurun_out/plain.log 2>&1 && \
