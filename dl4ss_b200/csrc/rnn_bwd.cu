@@ -314,7 +314,8 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
             Wt[(size_t)(BM_NP + j) * pitch + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
         }
         if (tid == 0) {
-            mbar_init(bar, 1);
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic zero fill before the bulk copies' writes
@@ -357,23 +358,30 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
 
         float dh = dyv;
         if (s > 0) {
-            if (warp == 0) {
+            // thread 0 watches the group counter; the tile's 32 row copies are then issued by lane 0 of every warp (two
+            // each): 32 copies from the lanes of ONE warp leave through the uniform datapath one after the other (~1 k cycles)
+            if (tid == 0) {
                 bm_stamp(p, s, 0);
-                if (lane == 0) {
-                    const unsigned want = (unsigned)p.nslices * (unsigned)s;
-                    while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
-                    mbar_expect_tx(bar, (uint32_t)(nrows * 2 * GHg * 2));
-                }
+                const unsigned want = (unsigned)p.nslices * (unsigned)s;
+                while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
+                mbar_expect_tx(&bar[0], (uint32_t)(nrows * 2 * GHg * 2));
+                mbar_arrive(&bar[1]);
                 bm_stamp(p, s, 1);
-                __syncwarp();
-                asm volatile("fence.proxy.async.global;\n" ::: "memory");   // the siblings' generic stores -> bulk-copy reads
-                const int r = lane >> 1, pl = lane & 1;
-                if (r < nrows)
-                    bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
-                             p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0 + r) * T + tl) * 2 + dir) * GHg,
-                             (uint32_t)(GHg * 2), bar);
             }
-            mbar_wait(bar, (uint32_t)(s - 1) & 1u);
+            mbar_wait(&bar[1], (uint32_t)(s - 1) & 1u);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.global;\n" ::: "memory");   // the siblings' generic stores -> bulk-copy reads
+#pragma unroll
+                for (int i = 0; i < 32 / BM_NW; ++i) {
+                    const int idx = warp * (32 / BM_NW) + i;
+                    const int r = idx >> 1, pl = idx & 1;
+                    if (r < nrows)
+                        bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
+                                 p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0 + r) * T + tl) * 2 + dir) * GHg,
+                                 (uint32_t)(GHg * 2), &bar[0]);
+                }
+            }
+            mbar_wait(&bar[0], (uint32_t)(s - 1) & 1u);
             bm_stamp(p, s, 2);
 
             float acc[3][4];
@@ -518,7 +526,7 @@ static int bwd_tc_pitch(int GH) {                                          // bf
 }
 static size_t bwd_tc_smem(int GH) {
     return (size_t)2 * (BM_NP + BW_BT) * bwd_tc_pitch(GH) * sizeof(__nv_bfloat16) +
-           (size_t)BM_NW * BW_BT * BM_NP * sizeof(float) + 16;
+           (size_t)BM_NW * BW_BT * BM_NP * sizeof(float) + 32;
 }
 
 template <int CELL>
