@@ -9,7 +9,8 @@
 //     for all T steps (104 KB at H = 600);
 //   * per (step, tile of 16 utterances) the product [16 x H] x [H x 40] runs on warp-level mma.sync.m16n8k16
 //     (bf16x3: hi*hi + hi*lo + lo*hi, fp32 accumulation).  K is split over the five MMA warps of a group, each warp
-//     against all five 8-column n-tiles, so one A fragment pair feeds 15 MMAs (28 shared-memory loads per k step; the
+//     against all five 8-column n-tiles, so one A fragment pair feeds 15 MMAs (fragments come in with ldmatrix: 8
+//     instructions, 28 shared-memory wavefronts per k step; the
 //     first form, one n-tile per warp over the whole K, needed 60 and ran at 84 % of the shared-memory pipe); the
 //     partial tiles meet in shared memory (two named barriers of the group's 160 threads), where every lane picks up
 //     the four gate pre-activations of ONE cell (16 rows x 10 units = 160 cells per group), adds the hoisted input
@@ -59,6 +60,14 @@ __device__ __forceinline__ void mm_mma(float (&d)[4], const uint32_t (&a)[4], ui
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four / two 8x8 b16 matrices: lane i supplies the 16-byte row address of row (i % 8) of matrix (i / 8)
+__device__ __forceinline__ void mm_ldsm4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mm_ldsm2(uint32_t &r0, uint32_t &r1, uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(saddr));
 }
 __device__ __forceinline__ void mm_bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -174,8 +183,15 @@ rnn_mma_kernel(const RnnMmaParams p) {
         const uint32_t *A32 = reinterpret_cast<const uint32_t *>(hb);
         const uint32_t *W32 = reinterpret_cast<const uint32_t *>(Wt);
         const int pw = pitch >> 1;
-        const uint32_t *bh = W32 + (size_t)fg * pw + ft;                // hi plane, n-tile 0, this lane's B column
-        const uint32_t *bl = bh + (size_t)MM_N * pw;
+        // ldmatrix row addresses (bytes, shared window).  A (16 x 16 of h): matrices (rows 0-7, k 0-7), (rows 8-15, k 0-7),
+        // (rows 0-7, k 8-15), (rows 8-15, k 8-15) = fragment registers a0..a3.  B (W, row = gate column n, k contiguous):
+        // matrices (n-tile j, k 0-7), (n-tile j, k 8-15), (n-tile j+1, k 0-7), (n-tile j+1, k 8-15) = b0, b1 of two n-tiles.
+        const int lrow = lane & 7, lmat = lane >> 3;
+        const uint32_t a_hi_addr = smem_u32(hb) + (uint32_t)(((lmat & 1) * 8 + lrow) * pitch + (lmat >> 1) * 8) * 2;
+        const uint32_t a_lo_addr = a_hi_addr + (uint32_t)(MM_BT * pitch) * 2;
+        const uint32_t b_hi_addr = smem_u32(Wt) + (uint32_t)(((lmat >> 1) * 8 + lrow) * pitch + (lmat & 1) * 8) * 2;
+        const uint32_t b_lo_addr = b_hi_addr + (uint32_t)(MM_N * pitch) * 2;
+        (void)A32; (void)W32; (void)pw;
         float *pmine = part + (size_t)(grp * MM_NT + wg) * (MM_BT * MM_N);
         const float *pgrp = part + (size_t)grp * MM_NT * (MM_BT * MM_N);
         // the cell this lane finishes: even ft -> row fg, odd ft -> row fg + 8; unit 2*wg + (ft >> 1)
@@ -205,24 +221,35 @@ rnn_mma_kernel(const RnnMmaParams p) {
                     for (int n = 0; n < MM_NT; ++n)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-                    const uint32_t *ah_p = A32 + (size_t)fg * pw + ft;
-                    const uint32_t *al_p = ah_p + (size_t)MM_BT * pw;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait(&hfull[2 * grp + h], ph_f);
                         const int ks1 = h ? p.nks : ks_half;
                         for (int ks = (h ? ks_half : 0) + wg; ks < ks1; ks += MM_NT) {
-                            const int kw = ks * 8;
+                            const uint32_t kb = (uint32_t)ks * 32;                 // bytes of 16 k
                             uint32_t ah[4], al[4];
-                            ah[0] = ah_p[kw]; ah[1] = ah_p[kw + 8 * pw]; ah[2] = ah_p[kw + 4]; ah[3] = ah_p[kw + 8 * pw + 4];
-                            al[0] = al_p[kw]; al[1] = al_p[kw + 8 * pw]; al[2] = al_p[kw + 4]; al[3] = al_p[kw + 8 * pw + 4];
+                            mm_ldsm4(ah, a_hi_addr + kb);
+                            mm_ldsm4(al, a_lo_addr + kb);
 #pragma unroll
-                            for (int n = 0; n < MM_NT; ++n) {
-                                const uint32_t bh0 = bh[8 * n * pw + kw], bh1 = bh[8 * n * pw + kw + 4];
-                                const uint32_t bl0 = bl[8 * n * pw + kw], bl1 = bl[8 * n * pw + kw + 4];
-                                mm_mma(acc[n], ah, bl0, bl1);
-                                mm_mma(acc[n], al, bh0, bh1);
-                                mm_mma(acc[n], ah, bh0, bh1);
+                            for (int n = 0; n < MM_NT; n += 2) {
+                                uint32_t bhv[4], blv[4];
+                                const uint32_t off = (uint32_t)(8 * n * pitch) * 2 + kb;
+                                if (n + 1 < MM_NT) {
+                                    mm_ldsm4(bhv, b_hi_addr + off);
+                                    mm_ldsm4(blv, b_lo_addr + off);
+                                } else {            // last, unpaired n-tile: lanes 16-31 supply (ignored) in-range addresses
+                                    mm_ldsm2(bhv[0], bhv[1], b_hi_addr + off - (uint32_t)((lmat >> 1) * 8 * pitch) * 2);
+                                    mm_ldsm2(blv[0], blv[1], b_lo_addr + off - (uint32_t)((lmat >> 1) * 8 * pitch) * 2);
+                                    bhv[2] = bhv[3] = blv[2] = blv[3] = 0u;
+                                }
+                                mm_mma(acc[n], ah, blv[0], blv[1]);
+                                mm_mma(acc[n], al, bhv[0], bhv[1]);
+                                mm_mma(acc[n], ah, bhv[0], bhv[1]);
+                                if (n + 1 < MM_NT) {
+                                    mm_mma(acc[n + 1], ah, blv[2], blv[3]);
+                                    mm_mma(acc[n + 1], al, bhv[2], bhv[3]);
+                                    mm_mma(acc[n + 1], ah, bhv[2], bhv[3]);
+                                }
                             }
                         }
                         __syncwarp();
