@@ -246,8 +246,9 @@ rnn_bwd_kernel(const RnnBwdParams p) {
 //   * W_hh^T slice resident in shared memory as bf16 hi/lo planes [2][24][pitch] (B fragments are plain 32-bit loads);
 //   * the gate gradients are exchanged as bf16 hi/lo planes (`xplanes` [2][B*T][2][GHg], the same 4 bytes per value
 //     as fp32), written by the owner threads next to the fp32 dgx / dgh the weight GEMMs read, so that A fragments
-//     need no conversion; a tile's 16 rows x 2 planes arrive as 32 bulk copies (cp.async.bulk, one per lane of
-//     warp 0) completing on an mbarrier: no per-thread cp.async issue, no wait_group + CTA barrier;
+//     need no conversion; a tile's 16 rows x 2 planes arrive as 32 bulk copies (cp.async.bulk) completing on an
+//     mbarrier, two issued by lane 0 of every warp once thread 0 has seen the group counter (the lanes of one warp would
+//     issue them one after the other through the uniform datapath): no per-thread cp.async, no wait_group + CTA barrier;
 //   * row pitch == 4 (mod 32) 32-bit words: the 8 rows x 4 k-pairs of a fragment load hit 32 different banks.
 constexpr int BM_NW = 16;
 constexpr int BM_THREADS = 32 * BM_NW;
