@@ -4,7 +4,7 @@ Public surface (names follow the reference, shincling/DL4SS):
     config                                   the globals the modules read
     MIX_SPEECH, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask      (modules.py)
     stft_features, mask_istft, prepare_batch                         (features.py)
-    Separator, mask_loss                                             (pipeline.py)
+    Separator, mask_loss, pit_mask_loss                              (pipeline.py)
     TrainStep, allreduce_gradients, shard_range                      (training.py)
 All compute goes through libdl4ss_b200.so (C ABI, include/dl4ss_b200.h); no CPU fallback.
 """
@@ -14,7 +14,7 @@ from .features import stft_features, mask_istft, prepare_batch, premix, window_t
 from .modules import (MIX_SPEECH, MIX_SPEECH_classifier, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
                       DeferredEmbedding, linear_fwd, linear_tc, split_bf16, weight_planes, rnn_forward,
                       emb_attn_mask, crm_decompress)
-from .pipeline import Separator, GraphedSeparator, HostPipeline, mask_loss  # noqa: F401
+from .pipeline import Separator, GraphedSeparator, HostPipeline, mask_loss, pit_mask_loss  # noqa: F401
 from .training import TrainStep, allreduce_gradients, shard_range  # noqa: F401
 
 __version__ = '0.1.0'

@@ -61,6 +61,7 @@ SIGNATURES = {
     'dl4ss_rnn_bwd_tc_supported': (c_i, [c_i, c_i]),
     'dl4ss_rnn_bwd_tc_xplanes_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'dl4ss_rnn_layer_bwd_tc': (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_sz, c_p]),
+    'dl4ss_mask_pair_loss_fwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     'dl4ss_mask_loss_fwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
 }
 

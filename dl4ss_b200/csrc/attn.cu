@@ -230,6 +230,119 @@ extern "C" int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float
     return DL4SS_OK;
 }
 
+// ------------------------------------------------------------------- permutation-invariant form of K5
+// pair[b][s][s'] = sum_tf |mask[b,s]*mix[b] - target[b,s']|^2 : every prediction against every target in one pass
+// over the masks, the mixture and the targets (the reference's loss pairs sources by sorted speaker index,
+// TDAA_beta/main_run_sstune_EvalVer.py:632-639; the permutation search over these S x S sums is the north-star's PIT
+// extension, oracle: oracle/modules_ref.py pit_mse_ref).  One CTA column per utterance, S <= 4.
+namespace dl4ss {
+constexpr int PIT_SMAX = 4;
+
+template <int MASK_KIND>
+__global__ void __launch_bounds__(256)
+mask_pair_loss_kernel(const float *__restrict__ mask, const float *__restrict__ mix, const float *__restrict__ target,
+                      int S, int TF, double *__restrict__ pair_out) {
+    const int b = blockIdx.y;
+    float e[PIT_SMAX][PIT_SMAX];
+#pragma unroll
+    for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+        for (int j = 0; j < PIT_SMAX; ++j) e[i][j] = 0.f;
+    double acc[PIT_SMAX][PIT_SMAX];
+#pragma unroll
+    for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+        for (int j = 0; j < PIT_SMAX; ++j) acc[i][j] = 0.0;
+    int n = 0;
+    for (int tf = blockIdx.x * blockDim.x + threadIdx.x; tf < TF; tf += gridDim.x * blockDim.x) {
+        if (MASK_KIND == DL4SS_MASK_REAL) {
+            const float x = mix[(size_t)b * TF + tf];
+            float pr[PIT_SMAX], y[PIT_SMAX];
+#pragma unroll
+            for (int s = 0; s < PIT_SMAX; ++s) {
+                pr[s] = (s < S) ? mask[((size_t)b * S + s) * TF + tf] * x : 0.f;
+                y[s] = (s < S) ? target[((size_t)b * S + s) * TF + tf] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+                for (int j = 0; j < PIT_SMAX; ++j) { const float d = pr[i] - y[j]; e[i][j] = fmaf(d, d, e[i][j]); }
+        } else {
+            const float2 x = reinterpret_cast<const float2 *>(mix)[(size_t)b * TF + tf];
+            float2 pr[PIT_SMAX], y[PIT_SMAX];
+#pragma unroll
+            for (int s = 0; s < PIT_SMAX; ++s) {
+                pr[s] = y[s] = make_float2(0.f, 0.f);
+                if (s < S) {
+                    const float2 m = reinterpret_cast<const float2 *>(mask)[((size_t)b * S + s) * TF + tf];
+                    pr[s] = make_float2(m.x * x.x - m.y * x.y, m.x * x.y + m.y * x.x);
+                    y[s] = reinterpret_cast<const float2 *>(target)[((size_t)b * S + s) * TF + tf];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+                for (int j = 0; j < PIT_SMAX; ++j) {
+                    const float dr = pr[i].x - y[j].x, di = pr[i].y - y[j].y;
+                    e[i][j] = fmaf(dr, dr, fmaf(di, di, e[i][j]));
+                }
+        }
+        if (++n == 64) {        // fold the fp32 partials into double before they grow
+#pragma unroll
+            for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+                for (int j = 0; j < PIT_SMAX; ++j) { acc[i][j] += (double)e[i][j]; e[i][j] = 0.f; }
+            n = 0;
+        }
+    }
+    __shared__ double red[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < PIT_SMAX; ++i)
+#pragma unroll
+        for (int j = 0; j < PIT_SMAX; ++j) {
+            if (i >= S || j >= S) continue;             // uniform
+            double v = acc[i][j] + (double)e[i][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (l == 0) red[w] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int k = 0; k < 8; ++k) t += red[k];
+                atomicAdd(pair_out + ((size_t)b * S + i) * S + j, t);
+            }
+        }
+}
+}  // namespace dl4ss
+
+extern "C" int dl4ss_mask_pair_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
+                                        int B, int S, int TF, double *pair_out, void *stream) {
+    DL4SS_CHECK_ARG(mask && mix && target && pair_out, "mask_pair_loss_fwd: null operand");
+    DL4SS_CHECK_ARG(mask_kind == DL4SS_MASK_REAL || mask_kind == DL4SS_MASK_COMPLEX, "mask_pair_loss_fwd: bad mask_kind %d", mask_kind);
+    DL4SS_CHECK_ARG(B >= 0 && S >= 1 && TF >= 1, "mask_pair_loss_fwd: bad shape");
+    if (S > PIT_SMAX) {
+        set_error("mask_pair_loss_fwd: S=%d exceeds the %d sources the kernel keeps in registers", S, PIT_SMAX);
+        return DL4SS_EUNSUPPORTED;
+    }
+    if (B == 0) return DL4SS_OK;
+    DL4SS_CHECK_ARG(B < 65536, "mask_pair_loss_fwd: B too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    DL4SS_CUDA(cudaMemsetAsync(pair_out, 0, (size_t)B * S * S * sizeof(double), st));
+    int chunks = cdiv(TF, 256 * 8);
+    const int cap = cdiv(sm_count() * 8, B);
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, B);
+    if (mask_kind == DL4SS_MASK_REAL)
+        mask_pair_loss_kernel<DL4SS_MASK_REAL><<<grid, 256, 0, st>>>(mask, mix, target, S, TF, pair_out);
+    else
+        mask_pair_loss_kernel<DL4SS_MASK_COMPLEX><<<grid, 256, 0, st>>>(mask, mix, target, S, TF, pair_out);
+    DL4SS_LAUNCH_CHECK("mask_pair_loss_kernel");
+    return DL4SS_OK;
+}
+
 // ------------------------------------------------------------------- a6 + a7: speaker queries
 // e = table[idx[b,s]]  (idx == NULL: table is already e[B,S,EQ]);
 // q[b,s,:] = residual*e + Wadj * [mean_t h[b,t,:] ; e]   (Wadj == NULL: q = e)

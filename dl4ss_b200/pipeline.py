@@ -227,3 +227,26 @@ def mask_loss(masks, mix, target, complex_mask=None):
     l0 = acc[0] / float(B * S * T * F)
     l1 = acc[1] / float(B * T * F)
     return l0 + 0.5 * l1, l0, l1
+
+
+def pit_mask_loss(masks, mix, target, complex_mask=None):
+    """Permutation-invariant MSE of mask x mixture against the targets (the north-star's PIT form of K5; the reference
+    pairs sources by sorted speaker index, TDAA_beta/main_run_sstune_EvalVer.py:632-639).
+
+    One kernel pass builds the S x S squared-error sums of every utterance (dl4ss_mask_pair_loss_fwd); the S! permutations
+    are searched on the device.  Returns (loss, perms): loss = mean over utterances of the best assignment's MSE (cRM:
+    MSE(Re) + MSE(Im)) as a 0-d CUDA float64 tensor, perms int64 [B,S] with perms[b,s] = the target matched to prediction s
+    (oracle: oracle/modules_ref.py pit_mse_ref)."""
+    import itertools
+    lib = _lib.load()
+    cplx = (masks.dim() == 5) if complex_mask is None else complex_mask
+    B, S, T, F = masks.shape[:4]
+    pair = torch.empty(B, S, S, device=masks.device, dtype=torch.float64)
+    rc = lib.dl4ss_mask_pair_loss_fwd(_lib.ptr(masks, name='masks'), _lib.MASK_COMPLEX if cplx else _lib.MASK_REAL,
+                                      _lib.ptr(mix, name='mix'), _lib.ptr(target, name='target'), B, S, T * F,
+                                      _lib.ptr(pair, torch.float64), _lib.stream())
+    _lib.check(rc, 'dl4ss_mask_pair_loss_fwd')
+    perms = torch.tensor(list(itertools.permutations(range(S))), device=masks.device)          # [P,S]
+    cost = pair[:, torch.arange(S, device=masks.device), perms].sum(-1) / float(S * T * F)          # [B,P]
+    best = cost.argmin(1)
+    return cost.gather(1, best[:, None]).mean(), perms[best]

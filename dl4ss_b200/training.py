@@ -154,7 +154,7 @@ class TrainStep(object):
                 'e': e, 'hmean': hmean, 'q': q, 'emb': emb, 'masks': masks, 'x0': mix_feas}
 
     # ------------------------------------------------------------------------------ loss + backward
-    def loss_and_grads(self, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, grad_scale=1.0):
+    def loss_and_grads(self, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, grad_scale=1.0, pit=False):
         """One forward + backward.  `global_batch`: utterances of the whole (all-rank) batch, so the
         MSELoss means -- and therefore the summed gradients -- are those of the global batch.
         Returns (loss, part0, part1) of THIS shard's contribution (sum over ranks = global loss)."""
@@ -167,6 +167,11 @@ class TrainStep(object):
             masks = ctx['masks']
             mix = mix_mag if cplx else mix_feas
             kind = _lib.MASK_COMPLEX if cplx else _lib.MASK_REAL
+            if pit:     # permutation-invariant training: the targets are re-ordered per utterance to the best assignment
+                from .pipeline import pit_mask_loss
+                _, perms = pit_mask_loss(masks, mix, target, cplx)
+                target = target[torch.arange(B, device=target.device)[:, None], perms].contiguous()
+                ctx['perms'] = perms
             acc = torch.zeros(2, device=masks.device, dtype=torch.float64)
             rc = lib.dl4ss_mask_loss_fwd(_lib.ptr(masks), kind, _lib.ptr(mix, name='mix'), _lib.ptr(target, name='target'),
                                          B, S, T * F, _lib.ptr(acc, torch.float64), _lib.stream())

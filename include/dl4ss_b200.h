@@ -206,6 +206,12 @@ int dl4ss_speaker_query_fwd(const float *h, int B, int T, int C, const float *ta
  * taken by the caller so shards of one global batch can be all-reduced first). */
 int dl4ss_mask_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
                         int B, int S, int TF, double *loss_out, void *stream);
+/* Permutation-invariant form: pair_out[b][s][s'] (double, [B,S,S], zeroed by the callee) = sum over T*F of
+ * |mask[b,s] x mix[b] - target[b,s']|^2 (cRM: real and imaginary squared errors summed), every prediction against every
+ * target in one pass; the caller searches the S! permutations (dl4ss_b200.pit_mask_loss).  The reference pairs sources
+ * by sorted speaker index (TDAA_beta/main_run_sstune_EvalVer.py:632-639); PIT is the north-star's extension.  S <= 4. */
+int dl4ss_mask_pair_loss_fwd(const float *mask, int mask_kind, const float *mix, const float *target,
+                             int B, int S, int TF, double *pair_out, void *stream);
 
 /* ---- a1: batched mixture synthesis ---------------------------------------------------------
  * The per-source preprocessing of the reference generators (TDAA_beta/predata_fromList.py:140-177):

@@ -166,3 +166,67 @@ def test_matmul_tn_split_k(cuda, R, Ca, Cb):
     many = M.linear_tc(ap, bp, bias, Ca, Cb, R, split_k=True)
     torch.cuda.synchronize()
     assert (one - many).abs().max().item() < 1e-4 * ref.abs().max().item()      # single-pass fp32 accumulation over all of K is the looser of the two
+
+
+@pytest.mark.parametrize('S,cplx', [(2, False), (3, False), (4, False), (3, True)])
+def test_pit_mask_loss_matches_oracle(cuda, S, cplx):
+    """dl4ss_mask_pair_loss_fwd + permutation search against the oracle's brute-force PIT (oracle/modules_ref.py
+    pit_mse_ref): loss value and the chosen assignment, with the targets of half the utterances shuffled."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    B, T, F = 6, 11, 129
+    g = torch.Generator().manual_seed(S + 10 * cplx)
+    if cplx:
+        masks = torch.randn(B, S, T, F, 2, generator=g)
+        mix = torch.randn(B, T, F, 2, generator=g)
+        pr = masks[..., 0] * mix[:, None, ..., 0] - masks[..., 1] * mix[:, None, ..., 1]
+        pi = masks[..., 0] * mix[:, None, ..., 1] + masks[..., 1] * mix[:, None, ..., 0]
+        pred = torch.stack([pr, pi], -1)
+    else:
+        masks = torch.rand(B, S, T, F, generator=g)
+        mix = torch.rand(B, T, F, generator=g) * 2
+        pred = masks * mix[:, None]
+    target = pred + 0.05 * torch.randn(pred.shape, generator=g)
+    true_perm = torch.stack([torch.randperm(S, generator=g) if b % 2 else torch.arange(S) for b in range(B)])
+    shuffled = torch.empty_like(target)
+    for b in range(B):
+        shuffled[b, true_perm[b]] = target[b]            # target s now sits at position true_perm[b][s]
+    ref_loss, ref_perm = mr.pit_mse_ref(pred, shuffled)
+    loss, perms = d.pit_mask_loss(masks.to(cuda).contiguous(), mix.to(cuda).contiguous(), shuffled.to(cuda).contiguous())
+    scale = 2.0 if cplx else 1.0                           # cRM: MSE(Re) + MSE(Im) = 2 x the mean over the stacked pair
+    assert abs(loss.item() - scale * ref_loss.item()) < 1e-6 * abs(ref_loss.item()) + 1e-9
+    assert torch.equal(perms.cpu(), ref_perm)
+    assert torch.equal(perms.cpu(), true_perm)
+
+
+def test_pit_training_gradients(cuda):
+    """TrainStep.loss_and_grads(pit=True): the gradients are those of the reference loss with the targets re-ordered to
+    the best assignment (autograd on the oracle with the oracle's own PIT assignment)."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    B, S, T = 4, 2, 13
+    ref, ours = build_pair('lstm', 1, 129, T, False)
+    torch.manual_seed(9)
+    feas = torch.rand(B, T, 129) * 2
+    idx = np.sort(np.random.RandomState(4).choice(101, (B, S)), axis=1)
+    r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, idx, None)
+    # targets = the current predictions pushed apart (source 0 up, source 1 down) plus noise, in swapped order for
+    # utterances 1 and 3: their best assignment is the swap
+    y = r['predict'].detach() * torch.tensor([1.5, 0.5]).view(1, S, 1, 1) + 0.02 * torch.rand(B, S, T, 129)
+    y[1] = y[1].flip(0)
+    y[3] = y[3].flip(0)
+    _, perm = mr.pit_mse_ref(r['predict'].detach(), y)
+    assert perm.tolist() == [[0, 1], [1, 0], [0, 1], [1, 0]]
+    y_perm = y[torch.arange(B)[:, None], perm]
+    loss = mr.loss_ref(ref['cfg'], r, y_perm)[0]
+    loss.backward()
+    g_ref = _grads(ref)
+    step = d.TrainStep(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    l, _, _ = step.loss_and_grads(feas.to(cuda), idx, y.to(cuda).contiguous(), None, pit=True)
+    assert abs(l.item() - loss.item()) < 1e-5 * abs(loss.item()) + 1e-8
+    g = _grads(ours)
+    for k, gr in g_ref.items():
+        if k.startswith('att.'):
+            continue
+        scale = max(gr.abs().max().item(), 1e-12)
+        assert (g[k] - gr).abs().max().item() / scale < 2e-3, k
