@@ -64,8 +64,15 @@ struct RnnTcParams {
     int trace_steps;
 };
 
-__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+// xproj is read exactly once: evict-first in L2, so that the 769 MB stream does not displace the layer's own output
+// (y and its bf16 planes, which the next projection reads)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "l"(pol) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
     unsigned v;
@@ -230,6 +237,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
         // ================= xproj prefetch (warps 11, 15): rows of step s into Xsm[tile][s&1]
         const int pt = (warp == 11 ? 0 : 32) + lane;
         constexpr int V = RT_HS / 4;                 // 16-byte chunks per (row, gate)
+        const uint64_t pol = l2_evict_first_policy();
         for (int s = 0; s < T; ++s) {
             const int buf = s & 1;
             const int t = dir ? (T - 1 - s) : s;
@@ -242,7 +250,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                     const int b = row0 + r;
                     if (b < p.B)
                         cp_async16_cg(dst + r * RT_XP + g * RT_HS + 4 * v,
-                                      p.xproj + (((size_t)b * T + t) * 2 + dir) * GH + (size_t)g * H + u0 + 4 * v);
+                                      p.xproj + (((size_t)b * T + t) * 2 + dir) * GH + (size_t)g * H + u0 + 4 * v, pol);
                 }
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
                 asm volatile("cp.async.wait_group 0;\n" ::: "memory");
