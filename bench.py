@@ -345,7 +345,7 @@ def run_reference(args):
             'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d utterances x 5 s per step (bounded sample of the batch-256 workload)' % n_utt},
             'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -422,11 +422,11 @@ def run_train(args):
         cfg['l2'] = 'working set >> 126 MB L2 (saved gates 192 MB/layer at 64 utterances)'
         cfg['launch'] = ('eager launches; the BPTT chain of each layer is one persistent kernel (dl4ss_rnn_layer_bwd_tc), '
                          'the forward recurrence one persistent kernel per layer (dl4ss_rnn_layer_tc_fwd)')
-        print(json.dumps({'metric': 'training_audio_seconds_per_second', 'value': audio_s / (ms * 1e-3), 'unit': 'audio-s/s',
+        emit({'metric': 'training_audio_seconds_per_second', 'value': audio_s / (ms * 1e-3), 'unit': 'audio-s/s',
                           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
                           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                           'data': 'synthetic', 'config': cfg, 'gpu_launches': launches, 'clocks': clocks,
-                          'loss': float(loss), 'parameters': nparams}))
+                          'loss': float(loss), 'parameters': nparams})
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -481,7 +481,27 @@ def workload_config(B):
             'launch': 'one CUDA graph per step (GraphedSeparator); the rotating batch is copied device-to-device into its static input inside the timed region'}
 
 
+RESULT = None     # the process's real stdout, reserved for the one JSON line
+
+
+def emit(line):
+    out = RESULT if RESULT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
+def reserve_stdout():
+    """Libraries print to stdout behind our back (NCCL's version banner at communicator creation): keep the real stdout
+    for the JSON line and point fd 1 at stderr for everything else."""
+    global RESULT
+    if RESULT is None:
+        sys.stdout.flush()
+        RESULT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -653,7 +673,7 @@ def main():
                         'd2h_bytes_per_step': bytes_out, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_stages': stages,
                 'cpu_baseline': cpu, 'configs3_training': train}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
