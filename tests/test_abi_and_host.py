@@ -187,3 +187,22 @@ def test_bss_closed_form_equals_oracle(S, perm):
         assert list(pm[b].numpy()) == list(o[3])
         for got, want in zip((sdr, sir, sar), o[:3]):
             assert np.abs(got[b].numpy() - want).max() < 1e-9
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU oracle arm the driver runs beside ours): stdout is exactly ONE JSON line carrying
+    the contract's keys, whatever else the run prints (library banners go to stderr)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--ref-utts', '1'], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['metric'] == 'separated_audio_seconds_per_second'
+    for k in ('value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'config', 'cpu_baseline', 'e2e'):
+        assert k in line, k
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['kind'] == 'port'
