@@ -4,9 +4,12 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <mutex>
 #include "../../include/dl4ss_b200.h"
 
 namespace dl4ss {
+
+constexpr int DL4SS_MAX_DEVICES = 64;
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

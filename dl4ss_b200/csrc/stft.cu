@@ -24,15 +24,32 @@ constexpr int K1_FT = 4 * K1_GROUPS;         // four frames per group (two packe
 __device__ float2 g_tw256[256];
 __global__ void init_twiddles_kernel() { fill_twiddles(g_tw256, threadIdx.x, blockDim.x); }
 
-static int ensure_twiddles(cudaStream_t st) {
-    static bool done[64] = {false};
+// Built exactly once per device, whatever host thread or stream gets here first (std::call_once per device): the table
+// is written on a private stream that is synchronised before the flag is set, so a launch on ANY stream that follows
+// sees it.  The capture-mode exchange keeps a first use inside a stream capture legal.
+static int ensure_twiddles(cudaStream_t) {
+    static std::once_flag once[DL4SS_MAX_DEVICES];
+    static int status[DL4SS_MAX_DEVICES];
     int dev = 0;
     DL4SS_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) dev = 63;
-    if (!done[dev] || dev == 63) {
-        init_twiddles_kernel<<<1, 256, 0, st>>>();
-        DL4SS_LAUNCH_CHECK("init_twiddles_kernel");
-        done[dev] = true;
+    DL4SS_CHECK_ARG(dev >= 0 && dev < DL4SS_MAX_DEVICES, "device ordinal %d out of range", dev);
+    std::call_once(once[dev], [dev]() {
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        cudaStream_t s = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (e == cudaSuccess) {
+            init_twiddles_kernel<<<1, 256, 0, s>>>();
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        status[dev] = (int)e;
+    });
+    if (status[dev] != 0) {
+        set_error("init_twiddles_kernel: %s", cudaGetErrorString((cudaError_t)status[dev]));
+        return DL4SS_ECUDA;
     }
     return DL4SS_OK;
 }

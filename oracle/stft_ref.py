@@ -34,6 +34,8 @@ def get_window(kind, n_fft):
             return np.sin(i * np.pi / n_fft)
         if kind == 'sqrt_hann':
             return np.sqrt(0.5 - 0.5 * np.cos(2.0 * np.pi * i / n_fft))
+        if kind == 'sqrt_hanning':                      # sqrt(np.hanning(M)): the SYMMETRIC Hann of the reference's own numpy
+            return np.sqrt(np.hanning(n_fft))           # stft/istft, Cocktail/software/DL4SS_Keras/test_stft_istft.py:9-10
         if kind == 'ones' or kind == 'boxcar':
             return np.ones(n_fft)
         raise ValueError('unknown window %r' % (kind,))
@@ -47,11 +49,21 @@ def num_frames(L, hop):
     return 1 + L // hop
 
 
-def stft_ref(y, n_fft=256, hop=128, window='hann', conj=False):
-    """y [L] real -> complex64 [F, T] (librosa layout)."""
+def stft_ref(y, n_fft=256, hop=128, window='hann', conj=False, center=True):
+    """y [L] real -> complex64 [F, T] (librosa layout).
+
+    center=False is the reference's own pure-numpy transform (Cocktail/software/DL4SS_Keras/test_stft_istft.py:13-35):
+    no padding, frames start at range(0, L - n_fft, hop) (a frame ending exactly at L is NOT taken), rfft of
+    window * frame, kept in complex128 as numpy does.  tests/golden/ref_stft_*.npz hold that function's outputs."""
     y = np.asarray(y, dtype=np.float64)
     if y.ndim != 1:
         raise ValueError('stft_ref takes one utterance')
+    if not center:
+        w = get_window(window, n_fft)
+        starts = np.arange(0, y.shape[0] - n_fft, hop)
+        idx = np.arange(n_fft)[:, None] + starts[None, :]
+        S = np.fft.rfft(y[idx] * w[:, None], axis=0)
+        return np.conj(S) if conj else S
     if y.shape[0] <= n_fft // 2:
         raise ValueError('reflect padding needs L > n_fft/2')
     w = get_window(window, n_fft)
@@ -75,12 +87,26 @@ def window_sumsquare(window, T, n_fft, hop):
     return x
 
 
-def istft_ref(S, hop=128, window='hann'):
-    """S complex [F, T] -> float32 [hop*(T-1)]."""
+def istft_ref(S, hop=128, window='hann', center=True):
+    """S complex [F, T] -> float32 [hop*(T-1)].
+
+    center=False is the reference's own pure-numpy inverse (Cocktail/software/DL4SS_Keras/test_stft_istft.py:38-63):
+    a float64 buffer of T*hop samples, frames n = 0.. placed at range(0, T*hop - n_fft, hop) (so the last n_fft/hop
+    frames are never used), irfft * window overlap-added, divided by the summed squared window where that is
+    non-zero; nothing is trimmed.  Returns float64 [T*hop]."""
     S = np.asarray(S)
     F, T = S.shape
     n_fft = 2 * (F - 1)
     w = get_window(window, n_fft)
+    if not center:
+        x = np.zeros(T * hop)
+        wsum = np.zeros(T * hop)
+        for n, i in enumerate(range(0, T * hop - n_fft, hop)):
+            x[i:i + n_fft] += np.fft.irfft(S[:, n]).real * w
+            wsum[i:i + n_fft] += w ** 2.0
+        pos = wsum != 0
+        x[pos] /= wsum[pos]
+        return x
     n = n_fft + hop * (T - 1)
     y = np.zeros(n, dtype=np.float32)
     full = np.concatenate([S, np.conj(S[-2:0:-1])], axis=0)     # [n_fft, T]
