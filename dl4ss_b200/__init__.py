@@ -6,6 +6,7 @@ Public surface (names follow the reference, shincling/DL4SS):
     stft_features, mask_istft, prepare_batch                         (features.py)
     Separator, mask_loss, pit_mask_loss                              (pipeline.py)
     TrainStep, allreduce_gradients, shard_range                      (training.py)
+    prepare_data, bss_eval, bss_eval_cRM, eval_bss, bss_test.cal      (compat.py: the reference's loop-level entry points)
 All compute goes through libdl4ss_b200.so (C ABI, include/dl4ss_b200.h); no CPU fallback.
 """
 from . import config  # noqa: F401
@@ -16,5 +17,8 @@ from .modules import (MIX_SPEECH, MIX_SPEECH_classifier, ATTENTION, SPEECH_EMBED
                       emb_attn_mask, crm_decompress)
 from .pipeline import Separator, GraphedSeparator, HostPipeline, mask_loss, pit_mask_loss  # noqa: F401
 from .training import TrainStep, allreduce_gradients, shard_range  # noqa: F401
+from . import compat  # noqa: F401
+from .compat import prepare_data, prepare_datasize, bss_eval, bss_eval_cRM, eval_bss, multi_label_vector  # noqa: F401
+from . import bss_test, predata_fromList  # noqa: F401
 
 __version__ = '0.1.0'

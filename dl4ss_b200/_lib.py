@@ -50,6 +50,7 @@ SIGNATURES = {
     'dl4ss_attn_dot_fwd': (c_i, [c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_speaker_query_fwd': (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
     'dl4ss_premix_fwd': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'dl4ss_premix_shift_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'dl4ss_xcorr_f64': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'dl4ss_mask_loss_bwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_attn_dot_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),

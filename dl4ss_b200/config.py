@@ -23,7 +23,13 @@ MAX_MIX = 2
 MAX_LEN = FRAME_RATE * 5    # 40000, :129-130
 WINDOWS = FRAME_LENGTH      # :133 (replaced by the sine table when init_config() runs, :240)
 IS_LOG_SPECTRAL = False     # :143
-Out_Sep_Result = True
+Out_Sep_Result = True         # bss_eval writes batch_output/*.wav (TDAA_beta/config_WSJ0_dB.py:153)
+# generator switches (TDAA_beta/config_WSJ0_dB.py:100-130); the reference's WSJ0 defaults are AUGMENT_DATA = True,
+# SHUFFLE_BATCH = True -- both off here so that a synthetic run is reproducible unless the caller turns them on
+AUGMENT_DATA = False
+SHUFFLE_BATCH = False
+Ground_truth = True
+dB = 5
 
 # cRM constants (TDAA_beta/main_run_sstune_cRM_EvalVer.py:28-29)
 cRM_k = 10.0

@@ -272,8 +272,8 @@ __device__ __forceinline__ float block_reduce(float v, float *red, bool is_max) 
 }
 
 __global__ void __launch_bounds__(512)
-premix_kernel(const float *__restrict__ src, const int *__restrict__ lengths, const float *__restrict__ gains_db,
-              int S, int L, float *__restrict__ src_out, float *__restrict__ mix_out) {
+premix_kernel(const float *__restrict__ src, const int *__restrict__ lengths, const int *__restrict__ shifts,
+              const float *__restrict__ gains_db, int S, int L, float *__restrict__ src_out, float *__restrict__ mix_out) {
     __shared__ float red[32];
     __shared__ float sc_mean[16], sc_scale[16];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -300,8 +300,14 @@ premix_kernel(const float *__restrict__ src, const int *__restrict__ lengths, co
         float m = 0.f;
         for (int s = 0; s < S; ++s) {
             int n = lengths ? lengths[b * S + s] : L;
+            n = n < 0 ? 0 : (n > L ? L : n);
             const size_t o = ((size_t)b * S + s) * L + i;
-            const float v = (i < n) ? (src[o] - sc_mean[s]) * sc_scale[s] : 0.f;
+            int j = i;
+            if (shifts && i < n) {                          // AUGMENT_DATA: signal = append(signal[shift:], signal[:shift])
+                j = i + shifts[b * S + s] % n;
+                j = j < 0 ? j + n : (j >= n ? j - n : j);
+            }
+            const float v = (i < n) ? (src[o - i + j] - sc_mean[s]) * sc_scale[s] : 0.f;
             if (src_out) src_out[o] = v;
             m += v;
         }
@@ -310,12 +316,18 @@ premix_kernel(const float *__restrict__ src, const int *__restrict__ lengths, co
 }
 }  // namespace dl4ss
 
-extern "C" int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
-                                float *src_out, float *mix_out, void *stream) {
+extern "C" int dl4ss_premix_shift_fwd(const float *src, const int *lengths, const int *shifts, const float *gains_db,
+                                      int B, int S, int L, float *src_out, float *mix_out, void *stream) {
     if (B == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG(src && gains_db && mix_out, "premix_fwd: null operand");
     DL4SS_CHECK_ARG(B >= 0 && S >= 1 && S <= 16 && L >= 1, "premix_fwd: bad B/S/L %d/%d/%d (S <= 16)", B, S, L);
-    premix_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(src, lengths, gains_db, S, L, src_out, mix_out);
+    DL4SS_CHECK_ARG(!(shifts && src_out == src), "premix_fwd: src_out may not alias src when shifts are given");
+    premix_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(src, lengths, shifts, gains_db, S, L, src_out, mix_out);
     DL4SS_LAUNCH_CHECK("premix_kernel");
     return DL4SS_OK;
+}
+
+extern "C" int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
+                                float *src_out, float *mix_out, void *stream) {
+    return dl4ss_premix_shift_fwd(src, lengths, nullptr, gains_db, B, S, L, src_out, mix_out, stream);
 }

@@ -148,18 +148,21 @@ def prepare_batch(mix_wav, n_fft=None, hop=None, is_log_spectral=None, window=No
     return out
 
 
-def premix(sources, gains_db, lengths=None, keep_sources=True):
+def premix(sources, gains_db, lengths=None, keep_sources=True, shifts=None):
     """GPU counterpart of the generators' per-source preprocessing + mixing
     (TDAA_beta/predata_fromList.py:140-177): sources [B,S,L] fp32 CUDA (raw, zero beyond `lengths`), gains_db
-    [B,S], lengths int [B,S] or None -> dict(mix_wav [B,L], sources [B,S,L] preprocessed) for `prepare_batch`."""
+    [B,S], lengths int [B,S] or None, shifts int [B,S] or None (the AUGMENT_DATA circular shift, :150-153)
+    -> dict(mix_wav [B,L], sources [B,S,L] preprocessed) for `prepare_batch`."""
     lib = _lib.load()
     B, S, L = sources.shape
     dev = sources.device
     gains_db = gains_db.to(device=dev, dtype=torch.float32).contiguous()
     ln = None if lengths is None else lengths.to(device=dev, dtype=torch.int32).contiguous()
+    sh = None if shifts is None else shifts.to(device=dev, dtype=torch.int32).contiguous()
     mix = torch.empty(B, L, device=dev, dtype=torch.float32)
     out = torch.empty_like(sources) if keep_sources else None
-    rc = lib.dl4ss_premix_fwd(_lib.ptr(sources, name='sources'), _lib.ptr(ln, torch.int32, 'lengths'),
-                              _lib.ptr(gains_db, name='gains_db'), B, S, L, _lib.ptr(out), _lib.ptr(mix), _lib.stream())
-    _lib.check(rc, 'dl4ss_premix_fwd')
+    rc = lib.dl4ss_premix_shift_fwd(_lib.ptr(sources, name='sources'), _lib.ptr(ln, torch.int32, 'lengths'),
+                                    _lib.ptr(sh, torch.int32, 'shifts'), _lib.ptr(gains_db, name='gains_db'), B, S, L,
+                                    _lib.ptr(out), _lib.ptr(mix), _lib.stream())
+    _lib.check(rc, 'dl4ss_premix_shift_fwd')
     return {'mix_wav': mix, 'sources': out}

@@ -537,12 +537,26 @@ class SPEECH_EMBEDDING(nn.Module):
             return mask_idx.to(device=self.layer.weight.device, dtype=torch.int64).contiguous()
         return torch.from_numpy(np.array(mask_idx, dtype=np.int64)).to(self.layer.weight.device)
 
-    def forward(self, input, mask_idx):
+    def forward(self, input, mask_idx=None):
+        if mask_idx is None:
+            return self.forward_multihot(input)
         idx = self.index_tensor(mask_idx)
         q, err = _speaker_query(None, self.layer.weight.detach(), idx, None, 1)
         if int(err.item()):
             raise IndexError('index out of range in self')     # nn.Embedding's error
         return q
+
+    def forward_multihot(self, input):
+        """The older one-argument form (Torch_multi/main_run_multi_selfSS.py:308-328): `input` [B,num_labels] is the
+        0/1 `top_k_mask`; every one of the num_labels channels gets a vector -- row (channel index x input) of the
+        table, i.e. the channel's own row where it is active and row 0 elsewhere -- multiplied by `input`, so
+        inactive channels are exactly zero.  -> [B,num_labels,E]."""
+        dev = self.layer.weight.device
+        inp = input.to(device=dev, dtype=torch.float32)
+        order = torch.arange(self.num_all, device=dev, dtype=torch.int64).unsqueeze(0)
+        idx = (order * inp.to(torch.int64)).contiguous()
+        q, _ = _speaker_query(None, self.layer.weight.detach(), idx, None, 1)
+        return q * inp.unsqueeze(-1)
 
 
 class ADDJUST(nn.Module):

@@ -48,17 +48,46 @@ class Separator(object):
 
     def masks(self, mix_feas, spk_idx, check_index=True):
         """mix_feas [B,T,F], spk_idx int [B,S] -> masks [B,S,T,F] (cRM: decompressed [B,S,T,F,2])."""
-        B, T, F = mix_feas.shape
         extras = {}
         hidden = self.mix.encode(mix_feas, extras)
+        return self.masks_from_hidden(hidden, extras, spk_idx, check_index)
+
+    def masks_from_hidden(self, hidden, extras, spk_idx, check_index=True):
+        """The part of `masks` after the encoder: speaker queries + the fused Linear/tanh/attention kernel."""
         q, err = self.queries(hidden, spk_idx, extras.get('hmean'))
         lin = self.mix.Linear
+        F = self.mix.input_fre
         E = lin.out_features // F
         out = M.emb_attn_mask(hidden, lin.weight, lin.bias, q, F, E,
                               complex_mask=self.complex_mask, decompress=True, h_planes=extras.get('planes'))
         self.last_err = err          # device flag of the embedding gather (GraphedSeparator.check_index reads it)
         if check_index and int(err.item()):
             raise IndexError('index out of range in self')
+        return out
+
+    def masks_multihot(self, mix_feas, top_k_mask_mixspeech):
+        """The older Torch_multi form (Torch_multi/main_run_multi_selfSS.py:476-493): one mask per candidate speaker,
+        `multi_mask * top_k_mask` -- channels the 0/1 selection `top_k_mask_mixspeech` [B,num_labels] switches off are
+        exactly zero, so only the active channels are evaluated (by the same fused kernel, ADDJUST not applied: that
+        script has none) and scattered into the [B,num_labels,T,F] result."""
+        sel = top_k_mask_mixspeech.to(device=mix_feas.device, dtype=torch.float32)
+        B, N = sel.shape
+        T, F = mix_feas.shape[1:]
+        count = sel.sum(1).to(torch.int64)
+        S = max(int(count.max().item()), 1)
+        order = torch.argsort(sel, 1, descending=True, stable=True)[:, :S]          # active channels first, by index
+        valid = torch.arange(S, device=sel.device)[None, :] < count[:, None]
+        idx = torch.where(valid, order, torch.zeros_like(order)).contiguous()
+        adj, self.adj = self.adj, None
+        try:
+            extras = {}
+            hidden = self.mix.encode(mix_feas, extras)                              # once; the fused kernel takes S <= 4 queries
+            m = torch.cat([self.masks_from_hidden(hidden, extras, idx[:, k:k + 4].contiguous()) for k in range(0, S, 4)], 1)
+        finally:
+            self.adj = adj
+        m = m * valid.to(m.dtype).view(B, S, *([1] * (m.dim() - 2)))
+        out = torch.zeros((B, N) + tuple(m.shape[2:]), device=m.device, dtype=m.dtype)
+        out.scatter_add_(1, idx.view(B, S, *([1] * (m.dim() - 2))).expand_as(m), m)
         return out
 
     def separate(self, mix_wav, spk_idx, return_all=False, check_index=True):

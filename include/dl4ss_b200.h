@@ -220,6 +220,12 @@ int dl4ss_mask_pair_loss_fwd(const float *mask, int mask_kind, const float *mix,
  * src) ; mix_out [B,L].  S <= 16. */
 int dl4ss_premix_fwd(const float *src, const int *lengths, const float *gains_db, int B, int S, int L,
                      float *src_out, float *mix_out, void *stream);
+/* The same with the AUGMENT_DATA circular shift of the training generators (TDAA_beta/predata_fromList.py:150-153,
+ * `signal = np.append(signal[shift:], signal[:shift])`, applied to the normalised signal BEFORE the zero padding):
+ * shifts [B,S] int (NULL: none), source (b,s) is rotated left by shifts[b,s] mod lengths[b,s] samples.  With shifts
+ * src_out must not alias src. */
+int dl4ss_premix_shift_fwd(const float *src, const int *lengths, const int *shifts, const float *gains_db,
+                           int B, int S, int L, float *src_out, float *mix_out, void *stream);
 
 /* ---- n2: short-lag cross-correlations for on-device BSS-Eval -----------------------------------
  * Replaces the FFT correlations inside mir_eval.separation.bss_eval_sources (`_compute_reference_correlations`,
