@@ -341,9 +341,11 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'separated_audio_seconds_per_second', 'value': v, 'unit': 'audio-s/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.batch),
-            'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d utterances x 5 s per step (bounded sample of the batch-256 workload)' % n_utt},
+            'config': dict(workload_config(args.batch), reference_sample_utterances_per_step=n_utt,
+                           launch='CPU: python loop over utterances for STFT/iSTFT (as the reference), torch-CPU modules on the %d-utterance sample' % n_utt,
+                           l2='n/a (CPU)'),
+            'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'cpu': cpu_model_name(), 'kind': 'port',
+                             'sample': '%d utterances x 5 s per step (bounded sample of the batch-256 workload: each step is %d of the 256 utterances)' % (n_utt, n_utt)},
             'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
     return 0
@@ -433,42 +435,170 @@ def run_train(args):
     return 0
 
 
-def training_extra(device, B=64, steps=5, warmup=3):
-    """BASELINE configs[3] on this GPU, reported next to the headline line (single-GPU runs only): the training step of
-    run_train() (STFTs -> forward with saved gates -> loss -> backward -> Adam) at B utterances, CUDA-event timed."""
+def training_extra(device, B=64, steps=5, warmup=3, dist=None, rank=0, world=1):
+    """BASELINE configs[3] next to the headline line, at every N: the training step of run_train() (STFTs -> forward
+    with saved gates -> loss -> backward -> gradient all-reduce -> Adam) at B utterances PER GPU (weak scaling), CUDA-event
+    timed, max over ranks.  At N > 1 the NCCL all-reduce of the gradient bucket is inside the timed step, launched per
+    layer segment underneath the rest of the backward pass; the same step is also timed with one serial all-reduce after
+    the backward pass and with no collective at all, so the cost of the exchange and what the overlap hides are visible."""
     import dl4ss_b200 as d
     W = WORKLOAD
-    sep = build_model(device)
+    sep = build_model(device)                       # same seed on every rank: identical replicas
     step = d.TrainStep(sep.mix, sep.emb, sep.att, sep.adj)
-    opt = torch.optim.Adam([{'params': step.parameters()}], lr=2e-4)
-    g = torch.Generator(device=device).manual_seed(11)
+    opt = torch.optim.Adam([{'params': step.parameters()}], lr=2e-4)       # EvalVer.py:537-544
+    g = torch.Generator(device=device).manual_seed(11 + rank)
     src = torch.randn(B, W['S'], W['L'], device=device, generator=g)
     src = src / src.abs().amax(2, keepdim=True)
     wav = src.sum(1).contiguous()
-    gi = torch.Generator().manual_seed(7)
+    gi = torch.Generator().manual_seed(7 + rank)
     idx = torch.sort(torch.stack([torch.randperm(W['num_spk'], generator=gi)[:W['S']] for _ in range(B)]), 1)[0].to(device)
 
-    def one_step():
+    def one_step(mode):
         batch = d.prepare_batch(wav, W['n_fft'], W['hop'], False, sources=src)
-        return step.step(opt, batch['mix_feas'], idx, batch['multi_spk_fea'].contiguous(), global_batch=B)
+        return step.step(opt, batch['mix_feas'], idx, batch['multi_spk_fea'].contiguous(), global_batch=B * world,
+                         overlap=(mode == 'overlap'), reduce=(mode != 'none'))
 
-    for _ in range(warmup):
-        one_step()
-    torch.cuda.synchronize()
-    n0 = d.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = one_step()[0]
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    out = {'workload': 'training step (BASELINE configs[3]): STFT -> BLSTM attention masks -> MSE loss -> backward -> Adam',
-           'batch_per_gpu': B, 'ms_per_step': ms, 'value': B * W['L'] / SR / (ms * 1e-3), 'unit': 'audio-s/s',
-           'steps': steps, 'warmup': warmup, 'gpu_launches_per_step': (d.launch_count() - n0) // steps, 'loss': float(loss)}
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(mode):
+        for _ in range(warmup):
+            one_step(mode)
+        barrier()
+        n0 = d.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one_step(mode)[0]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, (d.launch_count() - n0) // steps, float(loss)
+
+    ms, launches, loss = timed('overlap')
+    out = {'workload': 'training step (BASELINE configs[3]): STFT -> BLSTM attention masks -> MSE loss -> backward -> gradient all-reduce -> Adam',
+           'batch_per_gpu': B, 'n_gpus': world, 'scaling': 'weak', 'ms_per_step': ms,
+           'value': world * B * W['L'] / SR / (ms * 1e-3), 'unit': 'audio-s/s', 'steps': steps, 'warmup': warmup,
+           'gpu_launches_per_step': launches, 'loss': loss,
+           'allreduce_bytes_per_step': step.reduced_bytes, 'allreduce_segments': len(step.bucket().ranges),
+           'collective': 'NCCL all-reduce (sum) of the persistent flat fp32 gradient bucket, one call per segment (head, then '
+                         'each recurrent layer top-down) launched as soon as the segment is written' if world > 1 else 'none (1 GPU)'}
+    if world > 1:
+        out['ms_per_step_serial_collective'] = timed('serial')[0]
+        out['ms_per_step_no_collective'] = timed('none')[0]
     del step, opt, sep, src, wav
     torch.cuda.empty_cache()
     return out
+
+
+def library_baseline(device, B, reps=3):
+    """The reference's OWN GPU lowering of the model stages, timed on this GPU ("the bar is the library-call
+    path"): torch.nn.LSTM (cuDNN persistent RNN) 4x300 bidirectional + nn.Linear + tanh writing the [B,T,F,E] tensor,
+    expand().contiguous() S-fold copy, baddbmm dot attention + sigmoid, mask x mixture
+    (TDAA_beta/main_run_sstune_EvalVer.py:282-303,216-226,453-470), fp32 with TF32 off.  The reference runs its STFT /
+    iSTFT on the CPU, so this comparator covers features -> masks -> predicted spectra only; it is compared with the sum
+    of our encoder + query + fused attention stages.  A comparator, not part of the product: plain torch, nothing of ours."""
+    W = WORKLOAD
+    T, F, H, E, S = 1 + W['L'] // W['hop'], W['n_fft'] // 2 + 1, W['H'], W['E'], W['S']
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(1)
+        rnn = torch.nn.LSTM(F, H, W['layers'], batch_first=True, bidirectional=True).to(device)
+        lin = torch.nn.Linear(2 * H, F * E).to(device)
+        table = torch.nn.Embedding(W['num_spk'], E).to(device)
+        adj = torch.nn.Linear(2 * H + E, E, bias=False).to(device)
+        feas = torch.rand(B, T, F, device=device) * 3
+        idx = torch.randint(0, W['num_spk'], (B, S), device=device)
+
+        def step():
+            x, _ = rnn(feas)
+            x = x.contiguous()
+            emb = torch.tanh(lin(x.view(B * T, -1))).view(B, T, F, E)
+            q = table(idx)
+            hm = torch.mean(x, 1).view(B, 1, 2 * H).expand(B, S, 2 * H)
+            q = adj(torch.cat([hm, q], 2)) + q
+            h5 = emb.view(B, 1, T, F, E).expand(B, S, T, F, E).contiguous().view(-1, T * F, E)
+            energy = torch.baddbmm(torch.zeros(B * S, T * F, 1, device=device), h5, q.view(B * S, E, 1))
+            mask = torch.sigmoid(energy).view(B, S, T, F)
+            return mask * feas.view(B, 1, T, F)
+
+        with torch.no_grad():
+            step()
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+        return {'ms_per_step': best, 'value': B * W['L'] / SR / (best * 1e-3), 'unit': 'audio-s/s', 'batch': B,
+                'what': 'torch.nn.LSTM (cuDNN) 4x300 + Linear + tanh + expand/contiguous + baddbmm + sigmoid + mask*mix, fp32 '
+                        '(TF32 off), features -> predicted spectra only (the reference runs STFT/iSTFT on the CPU)',
+                'torch': torch.__version__, 'cudnn': torch.backends.cudnn.version()}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+
+
+def cpu_model_name():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.lower().startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def cpu_batched_baseline(n_utt, budget_s=12.0):
+    """A CPU baseline that is NOT a strawman: the same model in plain torch on all host cores, but batched the way a
+    careful CPU implementation would be -- ONE torch.stft over the batch (no per-utterance python loop, no redundant second
+    and third mixture STFT), the modules on the whole batch, one batched torch.istft.  Bounded sample of the workload."""
+    W = WORKLOAD
+    T, F, H, E, S = 1 + W['L'] // W['hop'], W['n_fft'] // 2 + 1, W['H'], W['E'], W['S']
+    torch.manual_seed(1)
+    rnn = torch.nn.LSTM(F, H, W['layers'], batch_first=True, bidirectional=True)
+    lin = torch.nn.Linear(2 * H, F * E)
+    table = torch.nn.Embedding(W['num_spk'], E)
+    adj = torch.nn.Linear(2 * H + E, E, bias=False)
+    wav = torch.randn(n_utt, W['L'])
+    idx = torch.randint(0, W['num_spk'], (n_utt, S))
+    win = torch.hann_window(W['n_fft'], periodic=True)
+
+    def step():
+        X = torch.stft(wav, W['n_fft'], W['hop'], W['n_fft'], win, center=True, pad_mode='reflect', return_complex=True)
+        feas = X.abs().transpose(1, 2).contiguous()                                     # [B,T,F]
+        x, _ = rnn(feas)
+        q = table(idx)
+        q = adj(torch.cat([x.mean(1, keepdim=True).expand(n_utt, S, 2 * H), q], 2)) + q
+        emb = torch.tanh(lin(x.reshape(n_utt * T, -1))).view(n_utt, T * F, E)
+        mask = torch.sigmoid(torch.bmm(emb, q.transpose(1, 2))).view(n_utt, T, F, S)      # no S-fold copy of the embedding
+        Y = mask.permute(0, 3, 2, 1) * X.unsqueeze(1)                                   # [B,S,F,T]
+        return torch.istft(Y.reshape(n_utt * S, F, T), W['n_fft'], W['hop'], W['n_fft'], win, center=True,
+                           length=W['hop'] * (T - 1))
+
+    with torch.no_grad():
+        step()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < 50):
+            step()
+            reps += 1
+        dt = time.perf_counter() - t0
+    return {'value': n_utt * W['L'] / SR * reps / dt, 'unit': 'audio-s/s', 'cores': torch.get_num_threads(), 'kind': 'port-batched',
+            'sample': '%d reps of one %d-utterance batch x 5 s: batched torch.stft / modules / torch.istft, no redundant STFTs' % (reps, n_utt)}
 
 
 def workload_config(B):
@@ -508,8 +638,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='utterances per GPU per step')
-    ap.add_argument('--ref-utts', type=int, default=16, help='utterances per step of the CPU reference arm')
+    ap.add_argument('--ref-utts', type=int, default=32, help='utterances per step of the CPU reference arm')
     ap.add_argument('--cpu-baseline-utts', type=int, default=4)
+    ap.add_argument('--cpu-batched-utts', type=int, default=32)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1: replay the step from one CUDA graph (default); 0: eager launches')
     ap.add_argument('--no-train-extra', action='store_true', help='skip the configs[3] training-step timing added to the line at N=1')
@@ -612,6 +743,13 @@ def main():
     value = audio_s / (ms * 1e-3)
     e2e_v = audio_s / (ms_e2e * 1e-3)
 
+    train = None
+    if not args.no_train_extra:          # every rank takes part: at N > 1 the NCCL gradient all-reduce is inside the timed step
+        try:
+            train = training_extra(device, dist=dist, rank=rank, world=world)
+        except Exception as e:           # the headline line must not depend on the extra measurement
+            train = {'error': repr(e)[:200]}
+
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -642,8 +780,16 @@ def main():
             stages[k] = {'bound': 'tensor', 'achieved': a, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                          'frac': a / peaks['bf16_tflops_sustained'], 'ms': st[k], 'flops': flops[k]}
         stages['query'] = {'ms': st['query']}
-        cpu = None
-        if not args.no_cpu_baseline:
+        cpu = cpu_batched = lib_base = None
+        if world == 1:
+            try:
+                lib_base = library_baseline(device, B)
+                ours_model_ms = st['rnn_xproj'] + st['rnn_recurrent'] + st['query'] + st['emb_attn_mask']
+                lib_base['ours_same_stages_ms'] = ours_model_ms
+                lib_base['speedup_vs_library'] = lib_base['ms_per_step'] / ours_model_ms
+            except Exception as e:
+                lib_base = {'error': repr(e)[:200]}
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (the other ranks would spin in a barrier meanwhile)
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             n_utt = args.cpu_baseline_utts
@@ -655,14 +801,13 @@ def main():
                 cpu_oracle_step(rc, mods, wav, cidx)
                 reps += 1
             dt = time.perf_counter() - t0
-            cpu = {'value': n_utt * W['L'] / SR * reps / dt, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port',
+            cpu = {'value': n_utt * W['L'] / SR * reps / dt, 'unit': 'audio-s/s', 'cores': cores, 'cpu': cpu_model_name(), 'kind': 'port',
                    'sample': '%d reps of %d utterances x 5 s (same model/config, bounded sample)' % (reps, n_utt)}
-        train = None
-        if world == 1 and not args.no_train_extra:
             try:
-                train = training_extra(device)
-            except Exception as e:       # the headline line must not depend on the extra measurement
-                train = {'error': repr(e)[:200]}
+                cpu_batched = cpu_batched_baseline(args.cpu_batched_utts)
+                cpu_batched['cpu'] = cpu['cpu']
+            except Exception as e:
+                cpu_batched = {'error': repr(e)[:200]}
         bytes_in = B * W['L'] * 4 + idx.numel() * 8
         bytes_out = B * W['S'] * Lout * 4
         line = {'metric': 'separated_audio_seconds_per_second', 'value': value, 'unit': 'audio-s/s',
@@ -672,7 +817,8 @@ def main():
                 'e2e': {'value': e2e_v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': bytes_in,
                         'd2h_bytes_per_step': bytes_out, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_stages': stages,
-                'cpu_baseline': cpu, 'configs3_training': train}
+                'cpu_baseline': cpu, 'cpu_baseline_batched': cpu_batched, 'library_baseline': lib_base,
+                'configs3_training': train}
         emit(line)
     if dist is not None:
         dist.barrier()

@@ -317,6 +317,29 @@ def crm_decompress(att):
     return -1 / config.cRM_C * torch.log((config.cRM_k - att) / (config.cRM_k + att))
 
 
+class _TrainsThroughTrainStep(torch.autograd.Function):
+    """Identity whose backward explains where the training path is.  The drop-in modules run hand-written forward
+    kernels on detached weights; the matching backward kernels are driven by `dl4ss_b200.TrainStep`, not by autograd."""
+
+    @staticmethod
+    def forward(ctx, x, anchor):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise RuntimeError('dl4ss_b200: the drop-in modules have no autograd graph -- loss.backward() cannot reach their '
+                           'parameters.  Run training steps through dl4ss_b200.TrainStep (forward + hand-written backward '
+                           'kernels + optimizer step), see INTEGRATION.md.')
+
+
+def _mark_no_autograd(out, param):
+    """Outside torch.no_grad() with trainable parameters: hang the loud backward on the output (evaluation loops that
+    never call backward are unaffected)."""
+    if torch.is_grad_enabled() and param.requires_grad and torch.is_tensor(out):
+        return _TrainsThroughTrainStep.apply(out, param)
+    return out
+
+
 # ----------------------------------------------------------------------------- deferred tensor
 class DeferredEmbedding(object):
     """Stand-in for MIX_SPEECH's [B,T,F,E] output that is never written to HBM.
@@ -415,6 +438,8 @@ class MIX_SPEECH(nn.Module):
         else:
             out = linear_fwd(xx.view(B * T, -1), self.Linear.weight.detach(), self.Linear.bias.detach(),
                              'tanh').view(B, T, F, E)
+        xx = _mark_no_autograd(xx, self.Linear.weight)
+        out = _mark_no_autograd(out, self.Linear.weight)
         return (out, xx) if self.return_hidden else out
 
 
@@ -422,8 +447,9 @@ class MIX_SPEECH_classifier(nn.Module):
     """MIX_SPEECH_classifier(input_fre, mix_speech_len, num_labels).forward(x[B,T,F]) -> speaker probabilities
     [B,num_labels]: BLSTM 3 x (2*HIDDEN_UNITS) -> mean over T -> Linear -> sigmoid
     (TDAA_beta/main_run_sstune_EvalVer.py:305-326).  The step before the separation path at
-    inference: `top_k_mask` of its output picks the speakers to extract.  H = 600 is outside the tcgen05 recurrent
-    kernel's range (W_hh would need 600 TMEM columns per plane), so the layers run on the fp32 persistent kernel."""
+    inference: `top_k_mask` of its output picks the speakers to extract.  H = 600 is outside the TMEM-resident
+    recurrent kernel's range (W_hh would need 600 TMEM columns per plane); its layers run on the batch-as-N tensor-core
+    recurrent kernel (dl4ss_rnn_layer_mma_fwd).  Inference only: there is no training path for the classifier."""
 
     def __init__(self, input_fre, mix_speech_len, num_labels):
         super(MIX_SPEECH_classifier, self).__init__()
@@ -440,7 +466,8 @@ class MIX_SPEECH_classifier(nn.Module):
         m = extras.get('hmean')
         if m is None:
             m = y.mean(1)                      # [B, 4*HIDDEN_UNITS]
-        return linear_fwd(m.contiguous(), self.Linear.weight.detach(), self.Linear.bias.detach(), 'sigmoid')
+        out = linear_fwd(m.contiguous(), self.Linear.weight.detach(), self.Linear.bias.detach(), 'sigmoid')
+        return _mark_no_autograd(out, self.Linear.weight)
 
 
 class ATTENTION(nn.Module):
@@ -470,7 +497,7 @@ class ATTENTION(nn.Module):
                 q = query.contiguous().view(B, S, -1)
                 out = emb_attn_mask(mix_hidden.hidden, mix_hidden.weight, mix_hidden.bias, q, F, E,
                                     complex_mask=cplx, decompress=False)
-                return out.view((B * S, T, F, 2) if cplx else (B * S, T, F))
+                return _mark_no_autograd(out.view((B * S, T, F, 2) if cplx else (B * S, T, F)), mix_hidden.weight)
             N, T, F, _ = mix_hidden.shape
             mix_hidden = mix_hidden.contiguous()
             q = query.contiguous().view(N, 1, -1)

@@ -137,14 +137,30 @@ class GraphedSeparator(object):
         gs = GraphedSeparator(sep, B, L, S)
         out = gs(wav, idx)          # copies into the static inputs, replays, returns the static output `gs.out`
     `gs.wav` / `gs.idx` / `gs.out` are static device tensors: fill the inputs in place and call `gs.replay()` to
-    skip the device-to-device copies; consume `gs.out` before the next replay.  Speaker indices are not range
-    checked inside the graph; `gs.check_index()` reads the gather kernel's error flag of the last replay."""
+    skip the device-to-device copies; consume `gs.out` before the next replay (and re-read `gs.out` after it: a
+    re-capture replaces the tensor).  Speaker indices are not range checked inside the graph; `gs.check_index()`
+    reads the gather kernel's error flag of the last replay.  The weights may change between replays (optimizer
+    step, load_state_dict): the graph is captured again when they do."""
 
     def __init__(self, separator, B, L, S, wav_dtype=torch.float32, device=None):
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.sep = separator
+        self.dev = dev
         self.wav = torch.zeros(B, L, device=dev, dtype=wav_dtype)
         self.idx = torch.zeros(B, S, device=dev, dtype=torch.int64)
+        self.captures = 0
+        self._capture()
+
+    def _param_key(self):
+        """(storage address, in-place version) of every parameter the captured kernels read.  The graph bakes in the
+        device pointers of operands DERIVED from the weights (bf16 planes, packed W_hh, concatenated W_ih): after an
+        optimizer step or load_state_dict those are stale, so `replay` re-captures when this key changes."""
+        sep = self.sep
+        mods = [sep.mix, sep.emb] + ([sep.adj] if sep.adj is not None else [])
+        return tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+
+    def _capture(self):
+        separator, dev = self.sep, self.dev
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
@@ -157,8 +173,13 @@ class GraphedSeparator(object):
             self.out = separator.separate(self.wav, self.idx, check_index=False)
             self.err = separator.last_err
         cur.wait_stream(side)
+        self.key = self._param_key()
+        self.captures += 1
 
     def replay(self):
+        if self._param_key() != self.key:      # weights changed since the capture (training between evaluations)
+            torch.cuda.current_stream(self.dev).synchronize()
+            self._capture()
         self.graph.replay()
         return self.out
 

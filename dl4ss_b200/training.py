@@ -34,44 +34,106 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def flatten_grads(params):
-    """One contiguous fp32 bucket of every parameter's gradient (zeros where a grad is None)."""
-    params = [p for p in params if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
-    o = 0
-    for p in params:
-        n = p.numel()
-        if p.grad is not None:
-            flat[o:o + n].copy_(p.grad.reshape(-1))
-        o += n
-    return flat
+def global_batch_size(local_b, device, group=None):
+    """Utterances of the whole step over all ranks (sum of the shard sizes; the local size without a process group):
+    the MSELoss means -- and so the summed gradients -- must be normalised by THIS, not by the shard size."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(local_b)
+    n = torch.tensor([int(local_b)], device=device, dtype=torch.int64)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    return int(n.item())
 
 
-def unflatten_grads(flat, params):
-    o = 0
-    for p in params:
-        if not p.requires_grad:
-            continue
-        n = p.numel()
-        g = flat[o:o + n].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
-        o += n
+class GradBucket(object):
+    """ONE persistent flat fp32 gradient buffer; every parameter's `.grad` is a VIEW into it, so gradients are written
+    in place by the backward kernels and reduced in place -- no flatten / unflatten copies, no per-step allocation.
+
+    The buffer is cut into SEGMENTS in the order the backward pass finishes them (the head: Linear + embedding +
+    ADDJUST, then the recurrent layers top-down).  `reduce_async(k)` launches the all-reduce (sum) of segment k as soon
+    as its gradients are written: the collective runs on the process group's own stream (NCCL over NVLink on the GPU
+    box, gloo in the CPU tests) underneath the BPTT chain and weight-gradient GEMMs of the layers below; `wait()` makes
+    the current stream wait for all of them before the optimizer step (bucket per layer to overlap with the
+    BPTT of lower layers)."""
+
+    def __init__(self, segments):
+        """segments: list of lists of parameters (requires_grad ones are kept)."""
+        self.segments = [[p for p in seg if p.requires_grad] for seg in segments]
+        params = [p for seg in self.segments for p in seg]
+        if not params:
+            raise ValueError('GradBucket: no trainable parameter')
+        self.params = params
+        self.flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=torch.float32)
+        self.views, self.ranges = [], []
+        o = 0
+        for seg in self.segments:
+            lo = o
+            for p in seg:
+                n = p.numel()
+                self.views.append(self.flat[o:o + n].view_as(p))
+                o += n
+            self.ranges.append((lo, o))
+        self.works = []
+        self.attach()
+
+    def attach(self):
+        """(Re-)install the views as the parameters' `.grad` (optimizer.zero_grad(set_to_none=True) drops them)."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+        self.attach()
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    def reduce_async(self, k, group=None):
+        """All-reduce (sum) segment k; returns immediately.  No-op without a process group / with one rank."""
+        import torch.distributed as dist
+        lo, hi = self.ranges[k]
+        if hi == lo or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 0
+        self.works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return (hi - lo) * 4
+
+    def reduce_all(self, group=None):
+        return sum(self.reduce_async(k, group) for k in range(len(self.ranges)))
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
+_buckets = {}
 
 
 def allreduce_gradients(params, group=None):
-    """Sum the gradients over ranks through ONE flat bucket (NCCL over NVLink on the GPU box, gloo in the
-    CPU tests).  Returns the number of bytes reduced.  No-op without an initialised process group."""
+    """Sum the gradients over ranks IN PLACE through one persistent flat bucket (created on the first call for this
+    parameter list; existing gradients are moved into it once).  Returns the number of bytes reduced.  No-op without
+    an initialised process group."""
     import torch.distributed as dist
     params = [p for p in params if p.requires_grad]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
-    flat = flatten_grads(params)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    unflatten_grads(flat, params)
-    return flat.numel() * 4
+    key = tuple(id(p) for p in params)
+    old = [p.grad for p in params]
+    b = _buckets.get(key)
+    if b is None:
+        _buckets.clear()                       # one parameter list at a time: drop the previous model's buffer
+        b = _buckets[key] = GradBucket([params])
+    b.attach()
+    for v, g in zip(b.views, old):             # gradients autograd (or anyone) left outside the bucket move in once
+        if g is None:
+            v.zero_()
+        elif g.data_ptr() != v.data_ptr():
+            v.copy_(g)
+    n = b.reduce_all(group)
+    b.wait()
+    return n
 
 
 def _mm_tn(a2d, b2d):
@@ -105,6 +167,32 @@ class TrainStep(object):
         self.adj = adjust_layer if (adjust_layer is not None and config.is_SelfTune) else None
         self.complex_mask = bool(config.is_ComlexMask)
         self._bptt = {}           # (layer, B, T) -> static buffers + captured BPTT graph
+        self._bucket = None       # GradBucket: created by step() on first use
+        self._reduce = None       # (bucket, group) while a step() wants its segments reduced as they complete
+        self.reduced_bytes = 0
+
+    def segments(self):
+        """Parameters in the order the backward pass completes their gradients: head (Linear, embedding table, ADDJUST),
+        then the recurrent layers from the top one down."""
+        rnn = self.mix.layer
+        head = list(self.mix.Linear.parameters()) + list(self.emb.parameters())
+        if self.adj is not None:
+            head += list(self.adj.parameters())
+        segs = [head]
+        for l in range(rnn.num_layers - 1, -1, -1):
+            segs.append([getattr(rnn, '%s_l%d%s' % (n, l, suf)) for suf in ('', '_reverse')
+                         for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')])
+        return segs
+
+    def bucket(self):
+        if self._bucket is None:
+            self._bucket = GradBucket(self.segments())
+        return self._bucket
+
+    def _segment_done(self, k):
+        if self._reduce is not None:
+            b, group = self._reduce
+            self.reduced_bytes += b.reduce_async(k, group)
 
     def parameters(self):
         mods = [self.mix, self.emb] + ([self.adj] if self.adj is not None else [])
@@ -225,6 +313,7 @@ class TrainStep(object):
         gt = torch.zeros_like(table)
         gt.index_add_(0, ctx['idx'].reshape(-1), de.reshape(B * S, EQ))
         _accum(table, gt)
+        self._segment_done(0)                  # head gradients complete: their all-reduce runs under the encoder backward
         # encoder backward, top layer first
         self.rnn_backward(ctx, dh.contiguous())
 
@@ -362,14 +451,29 @@ class TrainStep(object):
                     _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)),
                            _mm_tn(dg_t.reshape(-1, G * H), h_prev.reshape(-1, H)))
                     _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
+            self._segment_done(rnn.num_layers - l)      # this layer's gradients: reduced under the layers below
             if l > 0:
                 dy = _mm_nn(dgx2d, lw['wih']).view(B, T, -1).contiguous()
 
     # ------------------------------------------------------------------------------ full step
-    def step(self, optimizer, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, group=None):
-        """zero_grad -> loss_and_grads -> all-reduce (if a process group is up) -> optimizer.step."""
-        optimizer.zero_grad(set_to_none=True)
-        out = self.loss_and_grads(mix_feas, spk_idx, target, mix_mag, global_batch)
-        allreduce_gradients(self.parameters(), group)
+    def step(self, optimizer, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, group=None, overlap=True,
+             reduce=True):
+        """zero the gradient bucket -> loss_and_grads -> all-reduce (if a process group is up; per segment, overlapped
+        with the rest of the backward pass unless overlap=False; reduce=False skips the collective: timing only) ->
+        optimizer.step.  `global_batch` defaults to the
+        sum of the shard sizes over the ranks."""
+        if global_batch is None:
+            global_batch = global_batch_size(mix_feas.shape[0], mix_feas.device, group)
+        b = self.bucket()
+        b.zero()
+        self.reduced_bytes = 0
+        self._reduce = (b, group) if (overlap and reduce) else None
+        try:
+            out = self.loss_and_grads(mix_feas, spk_idx, target, mix_mag, global_batch)
+        finally:
+            self._reduce = None
+        if reduce and not overlap:
+            self.reduced_bytes = b.reduce_all(group)
+        b.wait()
         optimizer.step()
         return out

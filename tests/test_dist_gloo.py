@@ -33,6 +33,22 @@ def _worker(rank, world, port, q):
         loss.backward()
         nbytes = allreduce_gradients(list(model.parameters()))
         flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        # the same through the persistent segmented bucket TrainStep.step uses: gradients are views, segments are
+        # reduced asynchronously in completion order, nothing is copied
+        from dl4ss_b200.training import GradBucket, global_batch_size
+        assert global_batch_size(hi - lo, torch.device('cpu')) == 7
+        bucket = GradBucket([list(model[1].parameters()), list(model[0].parameters())])
+        ptr = bucket.flat.data_ptr()
+        for _ in range(2):                                     # two steps: the buffer and the views persist
+            bucket.zero()
+            loss = ((model(xs[lo:hi]) - ys[lo:hi]) ** 2).sum() / (7 * 3)
+            loss.backward()
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+            n2 = bucket.reduce_async(0) + bucket.reduce_async(1)
+            bucket.wait()
+        assert bucket.flat.data_ptr() == ptr and n2 == nbytes == bucket.nbytes
+        flat2 = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        assert torch.allclose(flat2, flat, atol=1e-7)
         q.put((rank, lo, hi, nbytes, flat.tolist()))
     finally:
         dist.destroy_process_group()

@@ -461,3 +461,49 @@ def test_on_device_bss_eval_matches_oracle(cuda, S):
     near = (ref[:, order] * 0.5 + 1e-4 * rng.randn(B, S, N)).astype(np.float32)
     s2, _, _, p2 = metrics.bss_eval_sources_batch(torch.from_numpy(ref).to(cuda), torch.from_numpy(near).to(cuda))
     assert s2.min().item() > 40.0 and list(p2[0].cpu().numpy()) == order
+
+
+@pytest.mark.gpu
+def test_graphed_separator_follows_weight_updates(cuda):
+    """the captured graph holds pointers to operands DERIVED from the weights (bf16 planes, packed W_hh).
+    After an in-place update (optimizer step) or load_state_dict the replay must use the new weights: the graph is
+    re-captured, and the result equals the eager path on the updated weights."""
+    import dl4ss_b200 as d
+    B, L, S = 6, 8000, 2
+    _, ours = build_pair('lstm', 2, 129, 63, False)
+    sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    g = torch.Generator(device='cuda').manual_seed(9)
+    wav = torch.randn(B, L, device=cuda, generator=g) * 0.3
+    idx = torch.sort(torch.stack([torch.randperm(101)[:S] for _ in range(B)]), 1)[0].to(cuda)
+    gs = d.GraphedSeparator(sep, B, L, S)
+    before = gs(wav, idx).clone()
+    assert gs.captures == 1 and torch.equal(before, sep.separate(wav, idx))
+    gs(wav, idx)
+    assert gs.captures == 1                                   # unchanged weights: no re-capture
+    with torch.no_grad():                                     # what optimizer.step() does
+        for p in ours['mix'].parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        ours['emb'].layer.weight.mul_(1.5)
+    after = gs(wav, idx).clone()
+    assert gs.captures == 2
+    eager = sep.separate(wav, idx)
+    assert torch.equal(after, eager) and (after - before).abs().max().item() > 1e-3
+    sd = {k: v.clone() * 0.5 for k, v in ours['mix'].state_dict().items()}
+    ours['mix'].load_state_dict(sd)
+    again = gs(wav, idx).clone()
+    assert gs.captures == 3 and torch.equal(again, sep.separate(wav, idx))
+
+
+@pytest.mark.gpu
+def test_modules_backward_is_loud(cuda):
+    """The drop-in modules carry no autograd graph: a reference-style loss.backward() must say where training lives
+    instead of silently leaving the parameters without gradients."""
+    import dl4ss_b200 as d
+    _, ours = build_pair('lstm', 1, 129, 8, False)
+    feas = torch.rand(2, 8, 129, device=cuda)
+    out, hid = ours['mix'](feas)
+    with pytest.raises(RuntimeError, match='TrainStep'):
+        hid.sum().backward()
+    with torch.no_grad():
+        out2, hid2 = ours['mix'](feas)
+    assert not hid2.requires_grad and torch.equal(hid2, hid.detach())

@@ -70,6 +70,12 @@ def test_train_step_reduces_loss(cuda):
     idx = np.array([[1, 5], [2, 9], [0, 7], [3, 4]])
     losses = [step.step(opt, feas, idx, y)[0].item() for _ in range(8)]
     assert losses[-1] < losses[0]
+    # the gradients live in ONE persistent bucket (views, no copies), cut into head + one segment per layer
+    b = step.bucket()
+    assert len(b.ranges) == 1 + 2 and b.ranges[-1][1] == b.flat.numel() == sum(p.numel() for p in step.parameters())
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views))
+    assert sorted(id(p) for p in b.params) == sorted(id(p) for p in step.parameters())
+    assert step.reduced_bytes == 0                            # one process: nothing to exchange
 
 
 def _bptt_step_chain(lib, L, cell, dy, whh, gates, cells, y, B, T, H, G):
