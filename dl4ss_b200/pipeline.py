@@ -75,7 +75,7 @@ class Separator(object):
         T, F = mix_feas.shape[1:]
         count = sel.sum(1).to(torch.int64)
         S = max(int(count.max().item()), 1)
-        order = torch.argsort(sel, 1, descending=True, stable=True)[:, :S]          # active channels first, by index
+        order = torch.argsort(sel, dim=1, descending=True, stable=True)[:, :S]          # active channels first, by index
         valid = torch.arange(S, device=sel.device)[None, :] < count[:, None]
         idx = torch.where(valid, order, torch.zeros_like(order)).contiguous()
         adj, self.adj = self.adj, None

@@ -93,6 +93,12 @@ def test_config2_gru_crm_three_speakers_across_launch_boundary(cuda):
     batch = synth.make_batch(B, L, S, seed=22)
     ref, ours = build_pair('gru', 2, 129, T, True)
     try:
+        # nn.Embedding's N(0,1) init with 2E = 100 wide queries puts ~5 % of the energies beyond |e| = 3, where the
+        # decompression amplifies the last ulp of tanh (the saturated end is test_crm_overflow's subject):
+        # scale the speaker table so that the masks sit in the range a trained cRM model uses
+        with torch.no_grad():
+            ref['emb'].layer.weight.mul_(0.25)
+            ours['emb'].layer.weight.mul_(0.25)
         feas, _, mag = _oracle_features(batch['mix_wav'][rows])
         with torch.no_grad():
             r = mr.forward_ref(ref['cfg'], ref['mix'], ref['emb'], ref['att'], ref['adj'], feas, batch['spk_idx'][rows], mag)
@@ -109,7 +115,8 @@ def test_config2_gru_crm_three_speakers_across_launch_boundary(cuda):
         assert e_mask < TOL, e_mask
         assert err[rm.abs() < 140.0].max().item() < 1e-2
         e_wav = rel_err(out['wav'][rows].cpu().numpy(), wav_ref)
-        print('configs[2] B=260: cRM mask err %.2e (|M|<60), wav err %.2e, max|M| %.1f' % (e_mask, e_wav, rm.abs().max().item()))
+        print('configs[2] B=260: cRM mask err %.2e (|M|<60: %.4f of the bins), wav err %.2e, max|M| %.1f'
+              % (e_mask, well.float().mean().item(), e_wav, rm.abs().max().item()))
         assert e_wav < TOL, e_wav
         assert not torch.isnan(out['wav']).any().item()
     finally:
