@@ -6,6 +6,7 @@
 // frames ride one complex transform (real/imag packing), and the 256-point transform runs on 16
 // lanes x 16 registers with one shared-memory transpose (fft256.cuh).
 #include "fft256x2.cuh"
+#include <stdlib.h>
 
 namespace dl4ss {
 
@@ -54,6 +55,26 @@ static int ensure_twiddles(cudaStream_t) {
     return DL4SS_OK;
 }
 
+// DL4SS_STAGED=0 in the environment selects the first-round direct-load kernels (A/B measurements)
+static bool staged_enabled() {
+    static const bool on = [] { const char *e = getenv("DL4SS_STAGED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// K1 is store dominated (3 output bytes per input byte) and runs best with the 16 resident warps of the direct-load form:
+// the staged K1 (12 warps per SM) measured 61 % against 67 % at the bench size, so it is opt-in (DL4SS_STAGED_K1=1)
+static bool staged_k1_enabled() {
+    static const bool on = [] { const char *e = getenv("DL4SS_STAGED_K1"); return e && e[0] == '1'; }();
+    return on;
+}
+// a persistent (looping) form of the direct-load K1 measured SLOWER than one item per CTA (59 % against 69 % at the bench
+// size, 59 % against 89 % at large batch): fresh CTAs overlap their load phase with their neighbours' store phase better
+// than a resident CTA walking its items in order; opt-in (DL4SS_PERSISTENT_K1=1)
+static bool persistent_k1_enabled() {
+    static const bool on = [] { const char *e = getenv("DL4SS_PERSISTENT_K1"); return e && e[0] == '1'; }();
+    return on;
+}
+
 // ------------------------------------------------------------------------------------ K1
 __device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT-class, max relative error 2^-23 (ftz: |X|^2 below 1.2e-38 reads as 0, far under eps)
     float r;
@@ -73,9 +94,67 @@ __device__ __forceinline__ float load_reflect(const WavT *__restrict__ w, int j,
     return (float)w[j];
 }
 
+// Output stage of K1: split the two packed complex transforms into four real-input spectra and store |X| / log|X| and
+// the complex rows.  v = the group's transforms after fft256x2_group; fr / ok = the four frames (clamped) and validity.
+template <int FEAT, bool CPLX>
+__device__ __forceinline__ void stft_store_rows(const cx2 (&v)[16], int l16, int b, int T, const int (&fr)[4], const bool (&ok)[4],
+                                                float eps, int conj, float *__restrict__ feat, float2 *__restrict__ cplx) {
+    // split Z = FFT(xa + i*xb) into the two real-input spectra (per transform):
+    //   XA[k] = (Z[k] + conj(Z[256-k]))/2 ,  XB[k] = (Z[k] - conj(Z[256-k]))/(2i)
+    // lane holds Z[16*k1+l16] in v[k1]; Z[256-k] lives in lane (16-l16)&15, register 15-k1
+    // (lane 0: own register (16-k1)&15).
+    size_t row[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[i] = ((size_t)b * T + fr[i]) * NBIN + l16;
+    const int src = (16 - l16) & 15;
+    const float sg = conj ? -0.5f : 0.5f;
+    const float2 half2 = pbc(0.5f), sgn2 = pbc(sg), nsgn2 = pbc(-sg);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        const cx2 z = v[k1];
+        cx2 p;
+        p.re.x = __shfl_sync(0xffffffffu, v[15 - k1].re.x, src, 16);
+        p.re.y = __shfl_sync(0xffffffffu, v[15 - k1].re.y, src, 16);
+        p.im.x = __shfl_sync(0xffffffffu, v[15 - k1].im.x, src, 16);
+        p.im.y = __shfl_sync(0xffffffffu, v[15 - k1].im.y, src, 16);
+        if (l16 == 0) p = v[(16 - k1) & 15];
+        // 2*XA = (sre, dim) ; 2*XB = (sim, -dre)
+        const float2 sre = padd(z.re, p.re), dim = psub(z.im, p.im), sim = padd(z.im, p.im), dre = psub(z.re, p.re);
+        if (FEAT != DL4SS_FEAT_NONE) {
+            const float2 qa = pfma(sre, sre, pmul(dim, dim)), qb = pfma(sim, sim, pmul(dre, dre));
+            float m[4] = {0.5f * sqrt_approx(qa.x), 0.5f * sqrt_approx(qb.x), 0.5f * sqrt_approx(qa.y), 0.5f * sqrt_approx(qb.y)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (FEAT == DL4SS_FEAT_LOG) m[i] = logf(m[i] + eps);
+                if (ok[i]) feat[row[i] + 16 * k1] = m[i];
+            }
+        }
+        if (CPLX) {
+            const float2 are = pmul(sre, half2), aim = pmul(dim, sgn2), bre = pmul(sim, half2), bim = pmul(dre, nsgn2);
+            if (ok[0]) cplx[row[0] + 16 * k1] = make_float2(are.x, aim.x);
+            if (ok[1]) cplx[row[1] + 16 * k1] = make_float2(bre.x, bim.x);
+            if (ok[2]) cplx[row[2] + 16 * k1] = make_float2(are.y, aim.y);
+            if (ok[3]) cplx[row[3] + 16 * k1] = make_float2(bre.y, bim.y);
+        }
+    }
+    if (l16 == 0) {   // Nyquist bin: Z[128] = XA[128] + i*XB[128], both real
+        const float x[4] = {v[8].re.x, v[8].im.x, v[8].re.y, v[8].im.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!ok[i]) continue;
+            if (FEAT != DL4SS_FEAT_NONE) {
+                float m = fabsf(x[i]);
+                if (FEAT == DL4SS_FEAT_LOG) m = logf(m + eps);
+                feat[row[i] + 128] = m;
+            }
+            if (CPLX) cplx[row[i] + 128] = make_float2(x[i], 0.0f);
+        }
+    }
+}
+
 template <typename WavT, int FEAT, bool CPLX, bool H128>
 __global__ void __launch_bounds__(K1_THREADS)
-stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt,
+stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt, int n_items,
                const float *__restrict__ window, float eps, int conj, int pf_dist,
                float *__restrict__ feat, float2 *__restrict__ cplx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,23 +163,27 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
     float *win = reinterpret_cast<float *>(tw + 256);                    // 256
 
     const int tid = threadIdx.x;
-    const int b = blockIdx.x / tiles_per_utt;
-    const int tile = blockIdx.x - b * tiles_per_utt;
-    const int t0 = tile * K1_FT;
-
-    // pull the waveform span of the CTA one resident wave ahead into L2 (no registers, no scoreboard): by the time
-    // that CTA runs, its loads are L2 hits instead of DRAM round trips
-    if (blockIdx.x + pf_dist < gridDim.x) {
-        const int pb = (blockIdx.x + pf_dist) / tiles_per_utt;
-        const int pt = (blockIdx.x + pf_dist) - pb * tiles_per_utt;
-        const int j = min(max(pt * K1_FT * hop - NFFT / 2 + tid * (int)(128 / sizeof(WavT)), 0), L - 1);
-        if (tid * (int)(128 / sizeof(WavT)) < (K1_FT - 1) * hop + NFFT) prefetch_l2(wav + (size_t)pb * L + j);
-    }
     for (int i = tid; i < NFFT; i += K1_THREADS) {
         tw[i] = g_tw256[i];
         win[i] = window[i];
     }
     __syncthreads();                       // twiddle / window tables: the kernel's only CTA-wide sync
+
+    // persistent form: gridDim.x < n_items, every CTA walks items blockIdx.x, + gridDim.x, ... (the tables above are
+    // built once, the last wave is one item long); gridDim.x == n_items is the one-item-per-CTA form
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / tiles_per_utt;
+    const int tile = item - b * tiles_per_utt;
+    const int t0 = tile * K1_FT;
+
+    // pull the waveform span of the item `pf_dist` ahead (the next resident wave / this CTA's next item) into L2 (no
+    // registers, no scoreboard): by the time it is processed, its loads are L2 hits instead of DRAM round trips
+    if (item + pf_dist < n_items) {
+        const int pb = (item + pf_dist) / tiles_per_utt;
+        const int pt = (item + pf_dist) - pb * tiles_per_utt;
+        const int j = min(max(pt * K1_FT * hop - NFFT / 2 + tid * (int)(128 / sizeof(WavT)), 0), L - 1);
+        if (tid * (int)(128 / sizeof(WavT)) < (K1_FT - 1) * hop + NFFT) prefetch_l2(wav + (size_t)pb * L + j);
+    }
 
     const int g = tid >> 4, l16 = tid & 15;
     const int f0 = t0 + 4 * g;
@@ -157,56 +240,7 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
     }
     fft256x2_group<false>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
 
-    // split Z = FFT(xa + i*xb) into the two real-input spectra (per transform):
-    //   XA[k] = (Z[k] + conj(Z[256-k]))/2 ,  XB[k] = (Z[k] - conj(Z[256-k]))/(2i)
-    // lane holds Z[16*k1+l16] in v[k1]; Z[256-k] lives in lane (16-l16)&15, register 15-k1
-    // (lane 0: own register (16-k1)&15).
-    size_t row[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) row[i] = ((size_t)b * T + fr[i]) * NBIN + l16;
-    const int src = (16 - l16) & 15;
-    const float sg = conj ? -0.5f : 0.5f;
-    const float2 half2 = pbc(0.5f), sgn2 = pbc(sg), nsgn2 = pbc(-sg);
-#pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) {
-        const cx2 z = v[k1];
-        cx2 p;
-        p.re.x = __shfl_sync(0xffffffffu, v[15 - k1].re.x, src, 16);
-        p.re.y = __shfl_sync(0xffffffffu, v[15 - k1].re.y, src, 16);
-        p.im.x = __shfl_sync(0xffffffffu, v[15 - k1].im.x, src, 16);
-        p.im.y = __shfl_sync(0xffffffffu, v[15 - k1].im.y, src, 16);
-        if (l16 == 0) p = v[(16 - k1) & 15];
-        // 2*XA = (sre, dim) ; 2*XB = (sim, -dre)
-        const float2 sre = padd(z.re, p.re), dim = psub(z.im, p.im), sim = padd(z.im, p.im), dre = psub(z.re, p.re);
-        if (FEAT != DL4SS_FEAT_NONE) {
-            const float2 qa = pfma(sre, sre, pmul(dim, dim)), qb = pfma(sim, sim, pmul(dre, dre));
-            float m[4] = {0.5f * sqrt_approx(qa.x), 0.5f * sqrt_approx(qb.x), 0.5f * sqrt_approx(qa.y), 0.5f * sqrt_approx(qb.y)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (FEAT == DL4SS_FEAT_LOG) m[i] = logf(m[i] + eps);
-                if (ok[i]) feat[row[i] + 16 * k1] = m[i];
-            }
-        }
-        if (CPLX) {
-            const float2 are = pmul(sre, half2), aim = pmul(dim, sgn2), bre = pmul(sim, half2), bim = pmul(dre, nsgn2);
-            if (ok[0]) cplx[row[0] + 16 * k1] = make_float2(are.x, aim.x);
-            if (ok[1]) cplx[row[1] + 16 * k1] = make_float2(bre.x, bim.x);
-            if (ok[2]) cplx[row[2] + 16 * k1] = make_float2(are.y, aim.y);
-            if (ok[3]) cplx[row[3] + 16 * k1] = make_float2(bre.y, bim.y);
-        }
-    }
-    if (l16 == 0) {   // Nyquist bin: Z[128] = XA[128] + i*XB[128], both real
-        const float x[4] = {v[8].re.x, v[8].im.x, v[8].re.y, v[8].im.y};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (!ok[i]) continue;
-            if (FEAT != DL4SS_FEAT_NONE) {
-                float m = fabsf(x[i]);
-                if (FEAT == DL4SS_FEAT_LOG) m = logf(m + eps);
-                feat[row[i] + 128] = m;
-            }
-            if (CPLX) cplx[row[i] + 128] = make_float2(x[i], 0.0f);
-        }
+    stft_store_rows<FEAT, CPLX>(v, l16, b, T, fr, ok, eps, conj, feat, cplx);
     }
 }
 
@@ -673,6 +707,8 @@ istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spe
 
 }  // namespace dl4ss
 
+#include "stft_staged.cuh"
+
 using namespace dl4ss;
 
 extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int n_fft, int hop,
@@ -694,22 +730,61 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
     const int T = 1 + L / hop;
     const int tiles = cdiv(T, K1_FT);
     const size_t smem = K1_GROUPS * DL4SS_XCH2_FLOAT4 * sizeof(float4) + 256 * sizeof(float2) + NFFT * sizeof(float);
-    const int pf_dist = 4 * sm_count();          // CTAs resident at once (4 per SM: registers / shared memory)
+    const int pf_dist = 4 * sm_count();          // CTAs resident at once (4 per SM: registers / shared memory; forcing 5 with 96 registers spills and measured 64 % against 69 %)
     const bool h128 = (hop == NFFT / 2);
     cudaStream_t st = (cudaStream_t)stream;
     { int rc = ensure_twiddles(st); if (rc) return rc; }
     const long long grid = (long long)B * tiles;
     DL4SS_CHECK_ARG(grid < (1ll << 31), "stft_feat: grid too large");
+    if (h128 && staged_k1_enabled() && (((uintptr_t)wav) & 15) == 0) {
+        // persistent CTAs fed by bulk copies (stft_staged.cuh)
+        const size_t esz = (wav_dtype == DL4SS_WAV_F32) ? sizeof(float) : sizeof(double);
+        const char *wav_end = (const char *)wav + (size_t)B * L * esz;
+#define LAUNCH_K1S(WT, FM, CP)                                                                                  \
+        do {                                                                                                    \
+            auto kern = stft256_staged_kernel<WT, FM, CP>;                                                      \
+            const size_t sm = K1S_STAGES * K1Stage<WT>::BYTES + K1_GROUPS * DL4SS_XCH2_FLOAT4 * sizeof(float4) + \
+                              256 * sizeof(float2) + NFFT * sizeof(float) + 2 * K1S_STAGES * sizeof(uint64_t) + 128; \
+            DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));       \
+            int per_sm = 0;                                                                                     \
+            DL4SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1S_THREADS, sm));          \
+            long long g = (long long)(per_sm > 0 ? per_sm : 1) * sm_count();                                    \
+            if (g > grid) g = grid;                                                                             \
+            kern<<<(unsigned)g, K1S_THREADS, sm, st>>>((const WT *)wav, L, T, tiles, (int)grid, wav_end, window, eps, conj, \
+                                                       feat_out, (float2 *)cplx_out);                          \
+        } while (0)
+#define DISPATCH_K1S(WT)                                                                                        \
+        do {                                                                                                    \
+            if (cplx_out) {                                                                                     \
+                if (feat_mode == DL4SS_FEAT_NONE) LAUNCH_K1S(WT, DL4SS_FEAT_NONE, true);                        \
+                else if (feat_mode == DL4SS_FEAT_ABS) LAUNCH_K1S(WT, DL4SS_FEAT_ABS, true);                     \
+                else LAUNCH_K1S(WT, DL4SS_FEAT_LOG, true);                                                      \
+            } else {                                                                                            \
+                if (feat_mode == DL4SS_FEAT_ABS) LAUNCH_K1S(WT, DL4SS_FEAT_ABS, false);                         \
+                else LAUNCH_K1S(WT, DL4SS_FEAT_LOG, false);                                                     \
+            }                                                                                                   \
+        } while (0)
+        if (wav_dtype == DL4SS_WAV_F32) DISPATCH_K1S(float);
+        else DISPATCH_K1S(double);
+#undef DISPATCH_K1S
+#undef LAUNCH_K1S
+        DL4SS_LAUNCH_CHECK("stft256_staged_kernel");
+        return DL4SS_OK;
+    }
+    // persistent form: one resident set of CTAs (4 per SM) walks the items
+    const bool pers = persistent_k1_enabled() && grid > pf_dist;
+    const long long grid_k1 = pers ? pf_dist : grid;
+    const int pf_k1 = pf_dist;
 #define LAUNCH_K1(WT, FM, CP)                                                                                  \
     do {                                                                                                        \
         if (h128) {                                                                                             \
             DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            stft256_kernel<WT, FM, CP, true><<<(unsigned)grid, K1_THREADS, smem, st>>>(                         \
-                (const WT *)wav, L, hop, T, tiles, window, eps, conj, pf_dist, feat_out, (float2 *)cplx_out);            \
+            stft256_kernel<WT, FM, CP, true><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                      \
+                (const WT *)wav, L, hop, T, tiles, (int)grid, window, eps, conj, pf_k1, feat_out, (float2 *)cplx_out);   \
         } else {                                                                                                \
             DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            stft256_kernel<WT, FM, CP, false><<<(unsigned)grid, K1_THREADS, smem, st>>>(                        \
-                (const WT *)wav, L, hop, T, tiles, window, eps, conj, pf_dist, feat_out, (float2 *)cplx_out);            \
+            stft256_kernel<WT, FM, CP, false><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                     \
+                (const WT *)wav, L, hop, T, tiles, (int)grid, window, eps, conj, pf_k1, feat_out, (float2 *)cplx_out);   \
         }                                                                                                       \
     } while (0)
 #define DISPATCH_K1(WT)                                                                                         \
@@ -756,6 +831,30 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
                                                  // ahead measured equal / slower (69.0 / 68.5 / 67.2 % at 5 s x 4096)
         const long long grid_h = (long long)B * ((S + 1) / 2) * tiles_h;
         DL4SS_CHECK_ARG(grid_h < (1ll << 31), "mask_istft: grid too large");
+        if (staged_enabled() && (((uintptr_t)spec) & 15) == 0 && (((uintptr_t)mask) & 15) == 0) {
+            // persistent CTAs fed by bulk copies (stft_staged.cuh)
+            const int pairs_tile = (mask_kind == DL4SS_MASK_COMPLEX) ? K6Cfg<DL4SS_MASK_COMPLEX>::PAIRS : K6Cfg<DL4SS_MASK_REAL>::PAIRS;
+            const int tiles_s = cdiv(T - 1, 2 * pairs_tile);         // a tile owns 2*PAIRS hop blocks
+            const long long items = (long long)B * ((S + 1) / 2) * tiles_s;
+            DL4SS_CHECK_ARG(items < (1ll << 31), "mask_istft: too many work items");
+            const char *spec_end = (const char *)spec + (size_t)B * (mask_kind == DL4SS_MASK_NONE ? S : 1) * T * NBIN * 8;
+            const char *mask_end = mask ? (const char *)mask + (size_t)B * S * T * NBIN * (mask_kind == DL4SS_MASK_COMPLEX ? 8 : 4) : nullptr;
+            const long long g = items < sm_count() ? items : sm_count();
+#define LAUNCH_K6S(KIND)                                                                                        \
+            do {                                                                                                \
+                auto kern = istft_h128_staged_kernel<KIND>;                                                     \
+                const size_t sm = K6Cfg<KIND>::SMEM;                                                            \
+                DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
+                kern<<<(unsigned)g, K6Cfg<KIND>::THREADS, sm, st0>>>(mask, (const float2 *)spec, S, T, tiles_s, (int)items, \
+                                                                     mask_end, spec_end, window, wav_out);      \
+            } while (0)
+            if (mask_kind == DL4SS_MASK_NONE) LAUNCH_K6S(DL4SS_MASK_NONE);
+            else if (mask_kind == DL4SS_MASK_REAL) LAUNCH_K6S(DL4SS_MASK_REAL);
+            else LAUNCH_K6S(DL4SS_MASK_COMPLEX);
+#undef LAUNCH_K6S
+            DL4SS_LAUNCH_CHECK("istft_h128_staged_kernel");
+            return DL4SS_OK;
+        }
 #define LAUNCH_H128(KIND)                                                                                       \
         do {                                                                                                    \
             DL4SS_CUDA(cudaFuncSetAttribute(istft_h128_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h)); \

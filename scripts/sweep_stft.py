@@ -14,15 +14,21 @@ from dl4ss_b200 import features
 ap = argparse.ArgumentParser()
 ap.add_argument('--out', default=None)
 ap.add_argument('--hop', type=int, default=128)
+ap.add_argument('--S', type=int, default=2)
+ap.add_argument('--crm', action='store_true', help='complex masks [B,S,T,F,2] (BASELINE configs[2])')
+ap.add_argument('--points', default=None, help='comma list of secs:batch')
 args = ap.parse_args()
 dev = torch.device('cuda:0')
 peak = 6548.8
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
 if os.path.exists(p):
     peak = json.load(open(p)).get('hbm_gbs', peak)
-S, hop = 2, args.hop
+S, hop = args.S, args.hop
 rows = []
 points = [(1, 1), (1, 64), (1, 4096), (5, 1), (5, 16), (5, 256), (5, 1024), (5, 4096), (30, 1), (30, 64), (30, 512)]
+if args.points:
+    points = [tuple(int(v) for v in q.split(':')) for q in args.points.split(',')]
+MB = 8 if args.crm else 4
 for secs, B in points:
     L = secs * 8000
     T, F = 1 + L // hop, 129
@@ -30,7 +36,7 @@ for secs, B in points:
     wavs = [torch.randn(B, L, device=dev) for _ in range(nbuf)]
     feat = [torch.empty(B, T, F, device=dev) for _ in range(2)]
     cplx = [torch.empty(B, T, F, 2, device=dev) for _ in range(2)]
-    masks = torch.rand(B, S, T, F, device=dev)
+    masks = torch.rand(B, S, T, F, 2, device=dev) if args.crm else torch.rand(B, S, T, F, device=dev)
     out = [torch.empty(B, S, hop * (T - 1), device=dev) for _ in range(2)]
     specs = []
     for w in wavs:
@@ -38,7 +44,7 @@ for secs, B in points:
         specs.append(c)
     fns = {'stft': lambda i: features.stft_features(wavs[i % nbuf], 256, hop, 'hann', 'abs', out_feat=feat[i % 2], out_cplx=cplx[i % 2]),
            'istft': lambda i: features.mask_istft(masks, specs[i % nbuf], hop, out=out[i % 2])}
-    byts = {'stft': B * (4 * L + 12 * T * F), 'istft': B * (4 * S * T * F + 8 * T * F + 4 * S * hop * (T - 1))}
+    byts = {'stft': B * (4 * L + 12 * T * F), 'istft': B * (MB * S * T * F + 8 * T * F + 4 * S * hop * (T - 1))}
     res = {}
     for name, fn in fns.items():
         fn(0); fn(1)
@@ -68,4 +74,4 @@ for secs, B, r in rows:
 txt = '\n'.join(lines)
 print(txt)
 if args.out:
-    open(args.out, 'w').write('# STFT / mask+iSTFT sweep (hop %d, S=%d), 1 B200, CUDA-graph replay timing\n\n' % (hop, S) + txt + '\n')
+    open(args.out, 'w').write('# STFT / mask+iSTFT sweep (hop %d, S=%d, %s masks), 1 B200, CUDA-graph replay timing\n\n' % (hop, S, 'complex (cRM)' if args.crm else 'real') + txt + '\n')
