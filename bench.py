@@ -275,6 +275,47 @@ def stage_times(sep, wav, idx, reps=3):
     return {n: float(np.median(v)) for n, v in acc.items()}
 
 
+def recurrent_concurrent_ms(sep, B, T, inflight, reps=3):
+    """Device time of the recurrent launches (all layers) of `inflight` batches running side by side on as many streams,
+    as they do in the timed region: CUDA events from the fork to the join.  Returns ms for the whole set."""
+    from dl4ss_b200 import _lib, modules as M
+    W = WORKLOAD
+    G, H = 4 if W['cell'] == 'lstm' else 3, W['H']
+    cell = _lib.CELL_LSTM if W['cell'] == 'lstm' else _lib.CELL_GRU
+    dev = next(sep.mix.parameters()).device
+    layers = sep.mix._packed.get()
+    Kpy = (2 * H + 63) // 64 * 64
+    sets = []
+    for _ in range(inflight):
+        sets.append({'xproj': torch.randn(B * T, 2 * G * H, device=dev) * 0.1,
+                     'ws': M.recurrent_workspace(B, T, H, cell, True, dev),
+                     'y': torch.empty(B, T, 2 * H, device=dev),
+                     'planes': torch.zeros(2, B * T, Kpy, device=dev, dtype=torch.bfloat16),
+                     'stream': torch.cuda.Stream(dev)})
+    best = 1e9
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream(dev)
+        e0.record()
+        for q in sets:
+            q['stream'].wait_event(e0)
+            with torch.cuda.stream(q['stream']):
+                for lw in layers:
+                    M.recurrent_layer(lw, cell, q['xproj'], B, T, H, q['ws'], True, None, None, q['y'], q['planes'], None)
+        for q in sets:
+            cur.wait_stream(q['stream'])
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def M_use_tc(W):
+    from dl4ss_b200 import _lib, modules as M
+    cell = _lib.CELL_LSTM if W['cell'] == 'lstm' else _lib.CELL_GRU
+    return bool(M.use_tc_recurrence(W['H'], cell))
+
+
 def algorithmic(B):
     """Algorithmic bytes / flops per step (SURVEY 8d figures x utterances per launch)."""
     W = WORKLOAD
@@ -601,6 +642,9 @@ def cpu_batched_baseline(n_utt, budget_s=12.0):
             'sample': '%d reps of one %d-utterance batch x 5 s: batched torch.stft / modules / torch.istft, no redundant STFTs' % (reps, n_utt)}
 
 
+INFLIGHT = 2          # steps in flight (set from --inflight)
+
+
 def workload_config(B):
     W = WORKLOAD
     return {'workload': W['name'], 'batch_per_gpu': B, 'utterance_s': W['L'] / SR, 'sample_rate': SR,
@@ -608,7 +652,7 @@ def workload_config(B):
             'encoder': '%s %dx%d bidirectional' % (W['cell'].upper(), W['layers'], W['H']),
             'embedding': W['E'], 'attention': 'dot + ADDJUST self-tune', 'mask': 'real sigmoid',
             'l2': 'working set >> 126 MB L2 (xproj 769 MB/layer at B=256) and 4 rotating input batches',
-            'launch': 'one CUDA graph per step (GraphedSeparator); the rotating batch is copied device-to-device into its static input inside the timed region'}
+            'launch': 'one CUDA graph per step; %d steps (256-utterance batches) in flight on as many streams (PipelinedSeparator / HostPipeline: the recurrent launches take 60 SMs per batch, so two batches share the GPU); the rotating batch is copied device-to-device into its static input inside the timed region' % INFLIGHT}
 
 
 RESULT = None     # the process's real stdout, reserved for the one JSON line
@@ -643,11 +687,17 @@ def main():
     ap.add_argument('--cpu-batched-utts', type=int, default=32)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=1, help='1: replay the step from one CUDA graph (default); 0: eager launches')
+    ap.add_argument('--inflight', type=int, default=2,
+                    help='steps (batches) in flight on as many streams in the inference timings (1: one batch owns the GPU)')
+    ap.add_argument('--e2e-depth', type=int, default=0, help='device slots of the end-to-end HostPipeline (0: inflight + 1)')
     ap.add_argument('--no-train-extra', action='store_true', help='skip the configs[3] training-step timing added to the line at N=1')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="'train': BASELINE configs[3], STFT -> encoder -> masks -> loss -> backward -> all-reduce -> Adam")
     ap.add_argument('--train-batch', type=int, default=64, help='utterances per GPU per training step')
     args = ap.parse_args()
+    global INFLIGHT
+    INFLIGHT = max(1, args.inflight)
+    args.inflight = INFLIGHT
     if args.impl == 'reference':
         return run_reference(args)
     if args.mode == 'train':
@@ -689,10 +739,30 @@ def main():
     n0 = d.launch_count()
     sep.separate(wavs[1 % len(wavs)], idx, check_index=False)
     launches_per_step = d.launch_count() - n0          # kernels of ours in one step (the graph replays exactly these)
-    step_fn = d.GraphedSeparator(sep, B, W['L'], W['S'], device=device) if args.graph else \
-        (lambda w, i: sep.separate(w, i, check_index=False))
+    if args.graph:
+        # `--inflight` 256-utterance batches on as many streams, one CUDA graph each (PipelinedSeparator); a step's result is
+        # picked up on the timing stream one submit later, as a consumer of the separated waveforms would
+        pipe_dev = d.PipelinedSeparator(sep, B, W['L'], W['S'], depth=args.inflight, device=device)
+        pending = []
+
+        def step_fn(w, i):
+            pending.append(pipe_dev.submit(w, i))
+            while len(pending) >= args.inflight:
+                k = pending.pop(0)
+                pipe_dev.result(k)
+                pipe_dev.release(k)
+
+        def finish():
+            while pending:
+                k = pending.pop(0)
+                pipe_dev.result(k)
+                pipe_dev.release(k)
+    else:
+        step_fn = lambda w, i: sep.separate(w, i, check_index=False)
+        finish = lambda: None
     for i in range(args.warmup):
         step_fn(wavs[i % len(wavs)], idx)
+    finish()
     if rank == 0:
         sampler.wait_first()
     barrier()
@@ -701,7 +771,8 @@ def main():
     sampler.begin()
     e0.record()
     for i in range(args.steps):
-        out = step_fn(wavs[i % len(wavs)], idx)
+        step_fn(wavs[i % len(wavs)], idx)
+    finish()
     e1.record()
     barrier()
     sampler.end()
@@ -714,21 +785,22 @@ def main():
     h_in = [w.cpu().pin_memory() for w in wavs]
     h_idx = idx.cpu().pin_memory()
     Lout = W['hop'] * (W['L'] // W['hop'])
-    h_outs = [torch.empty(B, W['S'], Lout, dtype=torch.float32).pin_memory() for _ in range(3)]
-    pipe = d.HostPipeline(sep, B, W['L'], W['S'], depth=2, device=device, graphs=bool(args.graph))
+    h_outs = [torch.empty(B, W['S'], Lout, dtype=torch.float32).pin_memory() for _ in range((args.e2e_depth or args.inflight + 1) + 1)]
+    pipe = d.HostPipeline(sep, B, W['L'], W['S'], depth=args.e2e_depth or args.inflight + 1, device=device, graphs=bool(args.graph),
+                          concurrent=args.inflight > 1)
     for i in range(max(8, args.warmup)):      # also lets the PCIe link leave its idle (down-trained) state
-        pipe.submit(h_in[i % 4], h_idx, h_outs[i % 3])
+        pipe.submit(h_in[i % 4], h_idx, h_outs[i % len(h_outs)])
     pipe.drain()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        pipe.submit(h_in[i % 4], h_idx, h_outs[i % 3])
+        pipe.submit(h_in[i % 4], h_idx, h_outs[i % len(h_outs)])
     pipe.drain()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    e2e_check = float(h_outs[(args.steps - 1) % 3].abs().max())      # the result really is on the host
+    e2e_check = float(h_outs[(args.steps - 1) % len(h_outs)].abs().max())      # the result really is on the host
     assert e2e_check > 0.0 and e2e_check == e2e_check
 
     if dist is not None:
@@ -753,13 +825,26 @@ def main():
     line = None
     if rank == 0:
         peaks = measured_peaks()
+        # stage times: one launch at a time with the whole GPU to itself (what the kernels themselves achieve); the timed
+        # region runs `inflight` batches side by side with the shared-SM geometry, measured for the dominant stage below
         st = stage_times(sep, wavs[0], idx)
+        rec_conc = None
+        if args.graph and args.inflight > 1 and M_use_tc(W):
+            with d.sm_sharing(*d.sm_sharing.PIPELINED):
+                rec_conc = recurrent_concurrent_ms(sep, B, 1 + W['L'] // W['hop'], 2)
         st.update(kernel_stage_times(sep, wavs, idx))
         alg = algorithmic(B)
         flops = {'rnn_xproj': alg['xproj_flops'], 'rnn_recurrent': alg['rec_flops'], 'emb_attn_mask': alg['emb_flops']}
         dom = max(flops, key=lambda k: st[k])
         n_launch = {'rnn_xproj': W['layers'], 'rnn_recurrent': W['layers'], 'emb_attn_mask': 1}[dom]
         ach = flops[dom] / (st[dom] * 1e-3) / 1e12
+        conc = None
+        if dom == 'rnn_recurrent' and rec_conc is not None:
+            # two batches' recurrent launches run side by side in the timed region (60 SMs each): the GPU-level figure is
+            # their joint work over their joint duration; the figure of one launch owning the GPU (80 SMs) is kept next to it
+            conc = {'batches': 2, 'ctas_per_launch': 60, 'ms_all_layers': rec_conc,
+                    'single_launch_achieved': ach, 'single_launch_frac': ach / peaks['bf16_tflops_sustained']}
+            ach = 2 * flops[dom] / (rec_conc * 1e-3) / 1e12
         tr = ncu_traffic({'rnn_recurrent': 'rnn_tc_kernel', 'rnn_xproj': 'EpiPlain', 'emb_attn_mask': 'EpiAttn'}[dom])
         roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
                 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
@@ -768,7 +853,7 @@ def main():
                 'algorithmic_bytes_per_launch': (B * (1 + W['L'] // W['hop']) * (2 * (4 if W['cell'] == 'lstm' else 3) * W['H'] * 4
                                                  + 2 * W['H'] * 4 + 2 * ((2 * W['H'] + 63) // 64 * 64) * 2)) if dom == 'rnn_recurrent' else None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
-                'launches_per_step': n_launch, 'ms_per_step': st[dom],
+                'launches_per_step': n_launch, 'ms_per_step': st[dom], 'concurrent': conc,
                 'note': 'algorithmic fp32 FLOPs; every tensor-core stage runs bf16x3 (3 MMA products per fp32 product); the recurrent stage is a latency chain of T sequential steps per layer, not throughput bound (DESIGN.md 4)'}
         stages = {}
         for k, by in (('stft', alg['stft_bytes']), ('mask_istft', alg['istft_bytes'])):

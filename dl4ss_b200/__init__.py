@@ -15,7 +15,7 @@ from .features import stft_features, mask_istft, prepare_batch, premix, window_t
 from .modules import (MIX_SPEECH, MIX_SPEECH_classifier, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
                       DeferredEmbedding, linear_fwd, linear_tc, split_bf16, weight_planes, rnn_forward,
                       emb_attn_mask, crm_decompress)
-from .pipeline import Separator, GraphedSeparator, HostPipeline, mask_loss, pit_mask_loss  # noqa: F401
+from .pipeline import Separator, GraphedSeparator, PipelinedSeparator, HostPipeline, sm_sharing, mask_loss, pit_mask_loss  # noqa: F401
 from .training import TrainStep, allreduce_gradients, shard_range  # noqa: F401
 from . import compat  # noqa: F401
 from .compat import prepare_data, prepare_datasize, bss_eval, bss_eval_cRM, eval_bss, multi_label_vector  # noqa: F401

@@ -34,6 +34,8 @@ SIGNATURES = {
     'dl4ss_rnn_layer_mma_fwd': (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     'dl4ss_rnn_tc_supported': (c_i, [c_i, c_i]),
     'dl4ss_rnn_tc_set_trace': (None, [c_p, c_i]),
+    'dl4ss_rnn_tc_set_tiles_per_cta': (None, [c_i]),
+    'dl4ss_gemm_tc_set_max_ctas': (None, [c_i]),
     'dl4ss_rnn_tc_whh_bytes': (c_sz, [c_i]),
     'dl4ss_rnn_tc_pack_whh': (c_i, [c_i, c_p, c_i, c_p, c_p]),
     'dl4ss_rnn_tc_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),

@@ -16,6 +16,7 @@
 // Tile 128 x 256 x 64, 2 smem stages x (A_hi,A_lo,B_hi,B_lo) = 192 KB, 2 TMEM accumulator stages x
 // 256 columns; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 #include <mutex>
 
 namespace dl4ss {
@@ -381,6 +382,18 @@ int make_bf16_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t
     return DL4SS_OK;
 }
 
+int make_f32_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                 const cuuint32_t *box) {
+    EncodeTiledFn fn = tensor_map_encoder();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DL4SS_ECUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (f32) failed (%d), rank %d", (int)r, rank); return DL4SS_ECUDA; }
+    return DL4SS_OK;
+}
+
 // planes: bf16 [2][R][Kp]; box = 64 (K) x rows x 1 plane, 128B swizzle, OOB rows zero-filled
 static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int Kp, int box_rows) {
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)R, 2};
@@ -403,6 +416,8 @@ static int pick_ksplit(long long tiles, int kblocks, int sms) {
     return best;
 }
 
+static int g_max_ctas = [] { const char *e = getenv("DL4SS_GEMM_MAX_CTAS"); return e ? atoi(e) : 0; }();
+
 template <typename Epi>
 static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, int K, int n_tiles, const Epi &epi,
                      cudaStream_t st, int nsplit = 1) {
@@ -415,6 +430,7 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
     const int m_tiles = cdiv(M, TBM);
     const long long total = (long long)m_tiles * n_tiles * nsplit;
     int grid = sm_count();
+    if (g_max_ctas > 0 && g_max_ctas < grid) grid = g_max_ctas;
     if (total < grid) grid = (int)total;
     auto kern = gemm_bf16x3_kernel<Epi>;
     DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -426,6 +442,8 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
 }  // namespace dl4ss
 
 using namespace dl4ss;
+
+extern "C" void dl4ss_gemm_tc_set_max_ctas(int ctas) { g_max_ctas = ctas; }
 
 extern "C" size_t dl4ss_split_bf16_bytes(long long R, int K) {
     if (R <= 0 || K <= 0) return 0;

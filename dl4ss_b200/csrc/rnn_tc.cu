@@ -24,25 +24,26 @@
 //     hides behind the other tile's MMA + gate math.  Groups never wait on each other; the launch is
 //     cooperative so every CTA is resident.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace dl4ss {
 
 constexpr int RT_NT = 32;                      // utterances per tile = UMMA N
-constexpr int RT_HS = 20;                      // hidden units per slice
-constexpr int RT_ROWS = 4 * RT_HS;             // W rows per slice in smem (GRU: 4th row of a unit is zero)
+constexpr int RT_HS = 32;                      // hidden units per slice: 4 gate rows x 32 units fill the 128 TMEM lanes
+constexpr int RT_ROWS = 4 * RT_HS;             // W rows per slice (GRU: 4th row of a unit is zero; units >= H: zero)
 constexpr int RT_KC = 64;                      // k per chunk (128 B of bf16: one swizzle row)
 constexpr int RT_MAXKC = 5;                    // H <= 320
-constexpr int RT_XP = 84;                      // xproj smem row pitch in floats
-constexpr int RT_TILES = 2;                    // tiles interleaved per CTA
+constexpr int RT_TILES = 3;                    // tiles interleaved per CTA
 constexpr int RT_TCOLS = 2 * RT_NT;            // TMEM accumulator columns per tile: hi*hi | hi*lo + lo*hi
 constexpr int RT_WCOL = RT_TILES * RT_TCOLS;   // first TMEM column of the resident W (A operand)
 constexpr int RT_WPLANE = RT_MAXKC * RT_KC / 2; // TMEM columns of one W plane (2 bf16 per column)
-constexpr int RT_EPI_PER_TILE = 6;             // epilogue warps per tile: 3 sub-partitions x 2 column halves
-constexpr int RT_PRE_THREADS = 64;             // xproj prefetch threads (warps 11, 15)
-constexpr int RT_THREADS = 512;
+constexpr int RT_EPI_PER_TILE = 8;             // epilogue warps per tile: 4 sub-partitions x 2 column halves
+constexpr int RT_EPI_WARPS = RT_TILES * RT_EPI_PER_TILE;     // warps [0, 16): epilogue (warp % 4 = TMEM sub-partition)
+constexpr int RT_W_MGR = RT_EPI_WARPS;         // warps 24..26: tile managers (h tile load + UMMA issue); warp 24 owns the TMEM allocation
+constexpr int RT_THREADS = 32 * (RT_EPI_WARPS + RT_TILES);
 constexpr int RT_WBLK = RT_ROWS * 128;         // bytes of one (k-chunk, plane) W block
 constexpr int RT_HBLK = RT_NT * 128;           // bytes of one (k-chunk, plane) h block
-constexpr int RT_XTILE = RT_NT * RT_XP;        // floats of one xproj buffer
+constexpr int RT_XTILE = RT_NT * 4 * RT_HS;    // floats of one xproj buffer: [utterance][gate][32 units], 128-byte rows, TMA 128B swizzle
 constexpr int RT_CTR_STRIDE = 64;              // uints between group counters: one 256-byte line each (atomics and the
                                                // pollers of different groups must not share an L2 line)
 
@@ -82,6 +83,11 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
 __device__ __forceinline__ void stamp(const RnnTcParams &p, int s, int slot) {
     if (p.trace != nullptr && blockIdx.x == 0 && s < p.trace_steps) p.trace[s * 16 + slot] = clock64();
 }
+__device__ __forceinline__ bool elect_one() {       // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 
 // branch-free select (selp): a chain of ?: on a lane-dependent index compiles to divergent branches
@@ -99,7 +105,7 @@ __device__ __forceinline__ float sel4(int k0, int k1, float a0, float a1, float 
 
 template <int CELL>
 __global__ void __launch_bounds__(RT_THREADS, 1)
-rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
+rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_x, const RnnTcParams p) {
     constexpr int G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
     constexpr uint32_t IDESC_HH = umma_idesc_bf16(128, 2 * RT_NT);   // W_hi x [h_hi ; h_lo]
     constexpr uint32_t IDESC_LH = umma_idesc_bf16(128, RT_NT);       // W_lo x h_hi
@@ -132,12 +138,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_h) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_x) : "memory");
         for (int i = 0; i < RT_TILES * RT_MAXKC; ++i) mbar_init(&hfull[i], 1);
         for (int i = 0; i < RT_TILES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], RT_EPI_PER_TILE); }
-        for (int i = 0; i < RT_TILES * 2; ++i) { mbar_init(&xfull[i], RT_PRE_THREADS); mbar_init(&xempty[i], RT_EPI_PER_TILE); }
+        for (int i = 0; i < RT_TILES * 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], RT_EPI_PER_TILE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 7) {
+    if (warp == RT_W_MGR) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,16 +154,17 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // resident A operand: TMEM lane = W row 32*warp + lane (row 4*u + g of the slice; rows >= 80 zero),
+        // resident A operand: TMEM lane = W row 32*warp + lane (row 4*u + g of the slice; units >= H zero),
         // column RT_WCOL + plane*RT_WPLANE + k/2 holds the bf16 pair (k, k+1)
         const int r = 32 * warp + lane;
+        const bool rvalid = u0 + (r >> 2) < H;
         const uint32_t ta = tmem_base + ((uint32_t)(32 * warp) << 16) + RT_WCOL;
         for (int pl = 0; pl < 2; ++pl) {
             const uint4 *src = reinterpret_cast<const uint4 *>(
-                p.wplanes + ((size_t)pl * 8 * H + (size_t)dir * 4 * H + 4 * u0 + (r < RT_ROWS ? r : 0)) * p.Kp);
+                p.wplanes + ((size_t)pl * 8 * H + (size_t)dir * 4 * H + 4 * u0 + (rvalid ? r : 0)) * p.Kp);
             for (int kk = 0; kk < p.Kp / 16; ++kk) {
                 uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-                if (r < RT_ROWS) { a = __ldg(src + 2 * kk); b = __ldg(src + 2 * kk + 1); }
+                if (rvalid) { a = __ldg(src + 2 * kk); b = __ldg(src + 2 * kk + 1); }
                 tmem_st8(ta + pl * RT_WPLANE + kk * 8, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
             }
         }
@@ -166,108 +174,89 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
     __syncthreads();
     tc_fence_after();
 
-    if (warp == 3) {
-        // ================= loader: h_{t-1} tiles as their groups publish them
-        if (lane == 0) {
+    if (warp >= RT_W_MGR && warp < RT_W_MGR + RT_TILES) {
+        // ================= tile manager (one warp per tile, one elected lane working): waits for the group's h_{t-1},
+        // TMA-loads the 32 x H tile (both planes, 5 k-chunks), issues the step's UMMAs, commits.
+        // acc[128 gate rows x 32 utterances] lives in two TMEM column blocks per tile.  UMMAs this small (128x64x16,
+        // 128x32x16) execute in ~70 cycles each whatever feeds them (measured: smem or TMEM A operand, split
+        // accumulators), so the count is kept at two per k step.  The issue path matters as much: the manager
+        // shares its scheduler with six epilogue warps, so (i) the working lane is chosen with elect.sync
+        // -- a `lane == 0` branch makes ptxas wrap every UTCHMMA in an elect/branch loop over the
+        // possibly-active lanes -- and (ii) every tile has its own manager on its own scheduler, so the three
+        // tiles' instruction streams are issued in parallel (one manager for all tiles issued a UMMA every ~115
+        // cycles instead of the tensor pipe's ~75).
+        const int tl = warp - RT_W_MGR;
+        if (tl < nt && elect_one()) {           // the other 31 lanes park at the final barrier
+            const uint64_t hdesc0 = umma_desc_sw128(smem_u32(Hsm + (size_t)tl * nkc * 2 * RT_HBLK));
+            unsigned char *hs = Hsm + (size_t)tl * nkc * 2 * RT_HBLK;
+            const uint32_t a_hi = tmem_base + RT_WCOL, a_lo = a_hi + RT_WPLANE;
+            const uint32_t d = tmem_base + tl * RT_TCOLS;
+            const int last_ksteps = (H - (nkc - 1) * RT_KC + 15) / 16;
             const unsigned per_step = (unsigned)(p.nslices * RT_EPI_PER_TILE);
+            const unsigned *ctr = counters + tl * RT_CTR_STRIDE;
+            // the hoisted input projection of step s: ONE 5-D TMA box [32 utterances][G gates][32 units] (fp32, evict-first:
+            // xproj is read exactly once) into Xsm[tile][s & 1]; columns >= H and utterances >= B arrive as zeros
+            const uint64_t xpol = l2_evict_first_policy();
+            auto load_x = [&](int s) {
+                const int buf = s & 1;
+                if (s >= 2) mbar_wait(&xempty[tl * 2 + buf], (uint32_t)((s >> 1) - 1) & 1u);
+                mbar_expect_tx(&xfull[tl * 2 + buf], RT_NT * G * RT_HS * 4);
+                tma_load_5d_hint(Xsm + (size_t)(tl * 2 + buf) * RT_XTILE, &tmap_x, &xfull[tl * 2 + buf], u0, 0, dir,
+                                 dir ? (T - 1 - s) : s, (tile_first + tl) * RT_NT, xpol);
+            };
+            load_x(0);
+            if (T > 1) load_x(1);
             for (int s = 1; s < T; ++s) {
                 const int z = (((s - 1) & 1) * 2 + dir) * 2;
-                for (int tl = 0; tl < nt; ++tl) {
-                    const unsigned want = per_step * (unsigned)s;
-                    if (tl == 0) stamp(p, s, 0);
-                    while (ld_acquire_gpu(counters + tl * RT_CTR_STRIDE) < want) { __nanosleep(40); }
-                    if (tl == 0) stamp(p, s, 1);
-                    fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
-                    unsigned char *hs = Hsm + (size_t)tl * nkc * 2 * RT_HBLK;
-                    for (int c = 0; c < nkc; ++c) {
-                        mbar_expect_tx(&hfull[tl * RT_MAXKC + c], 2 * RT_HBLK);     // one box = both planes of the chunk
-                        tma_load_3d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], c * RT_KC,
-                                    (tile_first + tl) * RT_NT, z);
-                    }
-                    if (tl == 0) stamp(p, s, 2);
+                const unsigned want = per_step * (unsigned)s;
+                if (tl == 0) stamp(p, s, 0);
+                while (ld_acquire_gpu(ctr) < want) { __nanosleep(40); }
+                if (tl == 0) stamp(p, s, 1);
+                fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
+                for (int c = 0; c < nkc; ++c) {
+                    mbar_expect_tx(&hfull[tl * RT_MAXKC + c], 2 * RT_HBLK);     // one box = both planes of the chunk
+                    tma_load_3d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], c * RT_KC,
+                                (tile_first + tl) * RT_NT, z);
                 }
-            }
-        }
-    } else if (warp == 7) {
-        // ================= MMA issuer: acc[128 gate rows x 32 utterances] in two column blocks per tile.
-        // UMMAs this small (128x64x16, 128x32x16) execute in ~70 cycles each whatever feeds them (measured:
-        // smem or TMEM A operand, one or two issuing threads, split accumulators), so the count is kept at two
-        // per k step and the issue path lean: descriptors built once, chunk / k loops fully unrolled with
-        // compile-time offsets and accumulate flags.
-        if (lane == 0) {
-            uint64_t hdesc0[RT_TILES];
+                if (tl == 0) stamp(p, s, 2);
+                if (s >= 2) { mbar_wait(&tempty[tl], (uint32_t)(s - 2) & 1u); tc_fence_after(); }
 #pragma unroll
-            for (int tl = 0; tl < RT_TILES; ++tl) hdesc0[tl] = umma_desc_sw128(smem_u32(Hsm + (size_t)tl * nkc * 2 * RT_HBLK));
-            const uint32_t a_hi = tmem_base + RT_WCOL, a_lo = a_hi + RT_WPLANE;
-            const int last_ksteps = (H - (nkc - 1) * RT_KC + 15) / 16;
-            for (int s = 1; s < T; ++s) {
+                for (int c = 0; c < RT_MAXKC; ++c) {
+                    if (c < nkc) {
+                        mbar_wait(&hfull[tl * RT_MAXKC + c], (uint32_t)(s - 1) & 1u);
+                        tc_fence_after();
+                        if (tl == 0 && c == 0) stamp(p, s, 3);
+                        if (tl == 0 && c == nkc - 1) stamp(p, s, 4);
+                        const uint64_t h_hi = hdesc0 + (uint64_t)((c * 2 * RT_HBLK) >> 4);
+                        const int ksteps = (c == nkc - 1) ? last_ksteps : RT_KC / 16;
 #pragma unroll
-                for (int tl = 0; tl < RT_TILES; ++tl) {
-                    if (tl < nt) {
-                        if (s >= 2) { mbar_wait(&tempty[tl], (uint32_t)(s - 2) & 1u); tc_fence_after(); }
-                        const uint32_t d = tmem_base + tl * RT_TCOLS;
-#pragma unroll
-                        for (int c = 0; c < RT_MAXKC; ++c) {
-                            if (c < nkc) {
-                                mbar_wait(&hfull[tl * RT_MAXKC + c], (uint32_t)(s - 1) & 1u);
-                                tc_fence_after();
-                                if (tl == 0 && c == 0) stamp(p, s, 3);
-                                if (tl == 0 && c == nkc - 1) stamp(p, s, 4);
-                                const uint64_t h_hi = hdesc0[tl] + (uint64_t)((c * 2 * RT_HBLK) >> 4);
-                                const int ksteps = (c == nkc - 1) ? last_ksteps : RT_KC / 16;
-#pragma unroll
-                                for (int k = 0; k < RT_KC / 16; ++k) {      // B: +32 B per k step (>>4 = 2); A: +8 columns
-                                    if (k < ksteps) {
-                                        const int kk = c * (RT_KC / 16) + k;
-                                        // W_hi x [h_hi ; h_lo] -> columns [0,64) ; then W_lo x h_hi onto [32,64)
-                                        if (c == 0 && k == 0) umma_bf16_ts<false>(d, a_hi, h_hi, IDESC_HH);
-                                        else umma_bf16_ts<true>(d, a_hi + kk * 8, h_hi + 2 * k, IDESC_HH);
-                                        umma_bf16_ts<true>(d + RT_NT, a_lo + kk * 8, h_hi + 2 * k, IDESC_LH);
-                                    }
-                                }
+                        for (int k = 0; k < RT_KC / 16; ++k) {      // B: +32 B per k step (>>4 = 2); A: +8 columns
+                            if (k < ksteps) {
+                                const int kk = c * (RT_KC / 16) + k;
+                                // W_hi x [h_hi ; h_lo] -> columns [0,64) ; then W_lo x h_hi onto [32,64)
+                                if (c == 0 && k == 0) umma_bf16_ts<false>(d, a_hi, h_hi, IDESC_HH);
+                                else umma_bf16_ts<true>(d, a_hi + kk * 8, h_hi + 2 * k, IDESC_HH);
+                                umma_bf16_ts<true>(d + RT_NT, a_lo + kk * 8, h_hi + 2 * k, IDESC_LH);
                             }
                         }
-                        umma_commit(&tfull[tl]);
-                        if (tl == 0) stamp(p, s, 5);
                     }
                 }
-            }
-        }
-    } else if ((warp & 3) == 3) {
-        // ================= xproj prefetch (warps 11, 15): rows of step s into Xsm[tile][s&1]
-        const int pt = (warp == 11 ? 0 : 32) + lane;
-        constexpr int V = RT_HS / 4;                 // 16-byte chunks per (row, gate)
-        const uint64_t pol = l2_evict_first_policy();
-        for (int s = 0; s < T; ++s) {
-            const int buf = s & 1;
-            const int t = dir ? (T - 1 - s) : s;
-            for (int tl = 0; tl < nt; ++tl) {
-                if (s >= 2) mbar_wait(&xempty[tl * 2 + buf], (uint32_t)((s >> 1) - 1) & 1u);
-                float *dst = Xsm + (size_t)(tl * 2 + buf) * RT_XTILE;
-                const int row0 = (tile_first + tl) * RT_NT;
-                for (int i = pt; i < RT_NT * G * V; i += RT_PRE_THREADS) {
-                    const int v = i % V, g = (i / V) % G, r = i / (V * G);
-                    const int b = row0 + r;
-                    if (b < p.B)
-                        cp_async16_cg(dst + r * RT_XP + g * RT_HS + 4 * v,
-                                      p.xproj + (((size_t)b * T + t) * 2 + dir) * GH + (size_t)g * H + u0 + 4 * v, pol);
-                }
-                asm volatile("cp.async.commit_group;\n" ::: "memory");
-                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-                mbar_arrive(&xfull[tl * 2 + buf]);
+                umma_commit(&tfull[tl]);
+                if (tl == 0) stamp(p, s, 5);
+                if (s + 1 < T) load_x(s + 1);       // its buffer was released two steps ago: never waits
             }
         }
     } else {
         // ================= epilogue: gates, state update, publish h_t
         const int sp = warp & 3;                     // TMEM sub-partition (lanes 32*sp..) this warp may read
-        const int j4 = warp >> 2;                    // 0..3
+        const int j4 = warp >> 2;                    // 0..RT_TILES*2-1
         const int tl = j4 >> 1;                      // tile served by this warp
         const int chalf = j4 & 1;                    // batch columns [16*chalf, 16*chalf+16) of the tile
         if (tl < nt) {
             const int g = lane & 3;                  // this lane's accumulator row is gate g of unit ul
             const int g0 = g & 1, g1 = g & 2;
             const int ul = 8 * sp + (lane >> 2);     // unit within the slice (row = 4*ul + g = 32*sp + lane)
-            const bool uvalid = ul < RT_HS;
+            const bool uvalid = u0 + ul < H;
             const int u = u0 + ul;
             const int row0 = (tile_first + tl) * RT_NT;
             const uint32_t taddr = tmem_base + ((uint32_t)(sp * 32) << 16) + tl * RT_TCOLS + chalf * 16;
@@ -320,12 +309,15 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
                 if (tr && lane == 0) stamp(p, s, 8);
                 mbar_wait(&xfull[tl * 2 + buf], (uint32_t)(s >> 1) & 1u);
                 if (tr && lane == 0) stamp(p, s, 11);
-                const float *xs = Xsm + (size_t)(tl * 2 + buf) * RT_XTILE + ul;
+                const float *xs = Xsm + (size_t)(tl * 2 + buf) * RT_XTILE;
                 float xv[4][G];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int gg = 0; gg < G; ++gg) xv[i][gg] = xs[bcol[i] * RT_XP + gg * RT_HS];
+                    for (int gg = 0; gg < G; ++gg) {
+                        const int row = bcol[i] * G + gg;                 // 128-byte row of the box; 16-byte chunks XOR (row & 7)
+                        xv[i][gg] = xs[row * RT_HS + ((((ul >> 2) ^ (row & 7)) << 2) | (ul & 3))];
+                    }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xempty[tl * 2 + buf]);
                 if (tr && lane == 0) stamp(p, s, 12);
@@ -418,7 +410,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const RnnTcParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 7) {
+    if (warp == RT_W_MGR) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -447,6 +439,7 @@ pack_whh_kernel(const float *__restrict__ whh, int G, int H, int Kp, __nv_bfloat
 
 static long long *g_trace = nullptr;
 static int g_trace_steps = 0;
+static int g_tiles_per_cta = [] { const char *e = getenv("DL4SS_RNN_TILES_PER_CTA"); return e ? atoi(e) : 0; }();
 
 template <int CELL>
 static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int tiles_left, cudaStream_t st, int *launched_tiles) {
@@ -462,10 +455,12 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int tiles_left, 
                   per_sm * sm_count(), p.nslices);
         return DL4SS_EUNSUPPORTED;
     }
-    // spread tiles over SMs first (one tile per CTA), then stack a second tile per CTA
+    // tiles per CTA: as few as the co-resident CTAs allow (shortest step), unless dl4ss_rnn_tc_set_tiles_per_cta asks
+    // for denser CTAs (fewer SMs per launch: two launches on different streams then run side by side)
     int ntiles = tiles_left;
     if (ntiles > max_groups * RT_TILES) ntiles = max_groups * RT_TILES;
-    const int tpg = (ntiles > max_groups) ? RT_TILES : 1;
+    int tpg = cdiv(ntiles, max_groups);
+    if (g_tiles_per_cta > tpg) tpg = g_tiles_per_cta < RT_TILES ? g_tiles_per_cta : RT_TILES;
     const int ngroups = cdiv(ntiles, tpg);
     p.ntiles = ntiles; p.tpg = tpg; p.ngroups = ngroups;
     *launched_tiles = ntiles;
@@ -479,13 +474,22 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int tiles_left, 
         int rc = make_bf16_map(&mh, p.hbuf, 3, dims, strides, box);
         if (rc) return rc;
     }
-    void *args[] = {(void *)&mh, (void *)&p};
+    CUtensorMap mx;
+    {   // xproj fp32 [B][T][2][G][H]: box = 32 units x G gates x 1 direction x 1 frame x 32 utterances
+        const cuuint64_t G = (CELL == DL4SS_CELL_LSTM) ? 4 : 3;
+        cuuint64_t dims[5] = {(cuuint64_t)p.H, G, 2, (cuuint64_t)p.T, (cuuint64_t)p.B};
+        cuuint64_t strides[4] = {(cuuint64_t)p.H * 4, G * p.H * 4, 2 * G * p.H * 4, (cuuint64_t)p.T * 2 * G * p.H * 4};
+        cuuint32_t box[5] = {RT_HS, (cuuint32_t)G, 1, 1, RT_NT};
+        int rc = make_f32_map(&mx, p.xproj, 5, dims, strides, box);
+        if (rc) return rc;
+    }
+    void *args[] = {(void *)&mh, (void *)&mx, (void *)&p};
     DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * ngroups * p.nslices), dim3(RT_THREADS), args, smem, st));
     count_launch();
     return DL4SS_OK;
 }
 
-static bool rnn_tc_supported(int H) { return H >= RT_HS && H % RT_HS == 0 && H <= RT_MAXKC * RT_KC; }
+static bool rnn_tc_supported(int H) { return H >= 4 && H % 4 == 0 && H <= RT_MAXKC * RT_KC; }
 
 }  // namespace dl4ss
 
@@ -496,6 +500,8 @@ extern "C" void dl4ss_rnn_tc_set_trace(void *dev_buf, int steps) {
     g_trace = (long long *)dev_buf;
     g_trace_steps = dev_buf ? steps : 0;
 }
+
+extern "C" void dl4ss_rnn_tc_set_tiles_per_cta(int tiles) { g_tiles_per_cta = tiles; }
 
 extern "C" int dl4ss_rnn_tc_supported(int H, int cell) {
     return (cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU) && rnn_tc_supported(H) ? 1 : 0;
@@ -536,11 +542,12 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
                                       void *workspace, size_t workspace_bytes, void *stream) {
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_tc_fwd: bad cell %d", cell);
     DL4SS_CHECK_ARG(xproj && whh_planes && y, "rnn_layer_tc_fwd: null operand");
+    DL4SS_CHECK_ARG((((uintptr_t)xproj) & 15) == 0, "rnn_layer_tc_fwd: xproj must be 16-byte aligned");
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || bhn, "rnn_layer_tc_fwd: GRU needs bhn");
     DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1, "rnn_layer_tc_fwd: bad B/T/H %d/%d/%d", B, T, H);
     if (!rnn_tc_supported(H)) {
-        set_error("rnn_layer_tc_fwd: H=%d unsupported (needs a multiple of %d, <= %d); use dl4ss_rnn_layer_fwd",
-                  H, RT_HS, RT_MAXKC * RT_KC);
+        set_error("rnn_layer_tc_fwd: H=%d unsupported (needs a multiple of 4, <= %d); use dl4ss_rnn_layer_fwd",
+                  H, RT_MAXKC * RT_KC);
         return DL4SS_EUNSUPPORTED;
     }
     if (B == 0) return DL4SS_OK;
@@ -561,7 +568,7 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
     p.Kp = p.nkc * RT_KC;
     p.Bpad = cdiv(B, RT_NT) * RT_NT;
     p.tiles_total = p.Bpad / RT_NT;
-    p.nslices = H / RT_HS;
+    p.nslices = cdiv(H, RT_HS);
     p.counters = (unsigned *)workspace;
     const size_t ctr = (size_t)2 * p.tiles_total * RT_CTR_STRIDE * sizeof(unsigned);
     p.hbuf = (__nv_bfloat16 *)((unsigned char *)workspace + ctr);

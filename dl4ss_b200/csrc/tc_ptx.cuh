@@ -40,6 +40,12 @@ __device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *map, 
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_hint(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                                 int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -118,5 +124,8 @@ EncodeTiledFn tensor_map_encoder();   // cuTensorMapEncodeTiled through the runt
 // bf16 tensor map, 128B swizzle, zero OOB fill; dims/box innermost first, strides (bytes) for dims 1..rank-1
 int make_bf16_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                   const cuuint32_t *box);
+// fp32 tensor map, 128B swizzle (inner box dimension = 32 floats), zero OOB fill
+int make_f32_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                 const cuuint32_t *box);
 
 }  // namespace dl4ss

@@ -164,7 +164,7 @@ class _PackedRNN(object):
 
 
 def use_tc_recurrence(H, cell):
-    """tcgen05 recurrent kernel: bf16x3 mode, supported H (multiple of 20, <= 320), not disabled."""
+    """tcgen05 recurrent kernel: bf16x3 mode, supported H (multiple of 4, <= 320), not disabled."""
     return (use_tensor_cores() and config.RNN_TENSOR_CORES
             and bool(_lib.load().dl4ss_rnn_tc_supported(H, cell)))
 

@@ -120,7 +120,7 @@ int    dl4ss_rnn_layer_mma_fwd(int cell, const float *xproj, const float *whh, c
  * whh [2,G*H,H] fp32 -> bf16 hi/lo planes [2][2 dir * 4H rows][Kp], row dir*4H + 4*u + g = gate g of
  * unit u (the unit-major order the kernel's epilogue transposes inside 4-lane groups; GRU's 4th row is
  * zero), dl4ss_rnn_tc_whh_bytes(H) bytes, 16-byte aligned.  Pack once per weight update.
- * Supported when dl4ss_rnn_tc_supported(H, cell) != 0 (H a multiple of 20, <= 320 -- every reference
+ * Supported when dl4ss_rnn_tc_supported(H, cell) != 0 (H a multiple of 4, <= 320 -- every reference
  * config uses 300); otherwise DL4SS_EUNSUPPORTED and the caller uses dl4ss_rnn_layer_fwd.
  * workspace: dl4ss_rnn_tc_workspace_bytes() bytes, 256-byte aligned, zero-filled by the callee
  * (release counters + the L2-resident bf16 exchange buffer the CTAs pass h_t through). */
@@ -128,6 +128,14 @@ int    dl4ss_rnn_tc_supported(int H, int cell);
 /* profiling hook: device buffer of steps*16 int64 that receives CTA 0's per-phase clock64() stamps of
  * subsequent dl4ss_rnn_layer_tc_fwd launches (NULL switches it off; off by default) */
 void   dl4ss_rnn_tc_set_trace(void *dev_buf, int steps);
+/* utterance tiles (32 utterances) a CTA of dl4ss_rnn_layer_tc_fwd interleaves: 0 = as few as the co-resident CTAs allow
+ * (shortest launch), 1..3 = at least that many (fewer CTAs per launch, so that launches on different streams run side by
+ * side).  Process-wide; initial value from the environment variable DL4SS_RNN_TILES_PER_CTA. */
+void   dl4ss_rnn_tc_set_tiles_per_cta(int tiles);
+/* persistent CTAs a tcgen05 projection launch (dl4ss_linear_tc_fwd, dl4ss_emb_attn_mask_tc_fwd, split-K form) may
+ * occupy: 0 = one per SM; n = at most n, so that two pipelined batches on different streams share the SMs (a recurrent
+ * launch of one batch next to a projection launch of the other).  Process-wide; initial value from DL4SS_GEMM_MAX_CTAS. */
+void   dl4ss_gemm_tc_set_max_ctas(int ctas);
 size_t dl4ss_rnn_tc_whh_bytes(int H);
 int    dl4ss_rnn_tc_pack_whh(int cell, const float *whh, int H, void *planes, void *stream);
 size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);

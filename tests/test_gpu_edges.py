@@ -92,7 +92,7 @@ def test_stft_istft_edge_lengths(cuda, hop, L):
 
 def test_errors_are_loud(cuda):
     import dl4ss_b200 as d
-    rnn, ours = _rnn_pair('lstm', 1, 304, 4)              # neither kernel has a 304-unit decomposition
+    rnn, ours = _rnn_pair('lstm', 1, 322, 4)              # no kernel has a 322-unit decomposition
     try:
         with pytest.raises(RuntimeError, match='multiple'):
             ours.encode(torch.zeros(2, 4, 129, device=cuda))
