@@ -12,7 +12,7 @@ All compute goes through libdl4ss_b200.so (C ABI, include/dl4ss_b200.h); no CPU 
 from . import config  # noqa: F401
 from ._lib import load as load_library, launch_count  # noqa: F401
 from .features import stft_features, mask_istft, prepare_batch, premix, window_tensor  # noqa: F401
-from .modules import (MIX_SPEECH, MIX_SPEECH_classifier, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
+from .modules import (MIX_SPEECH, MIX_SPEECH_classifier, Discriminator, gan_loss_terms, ATTENTION, SPEECH_EMBEDDING, ADDJUST, top_k_mask,  # noqa: F401
                       DeferredEmbedding, linear_fwd, linear_tc, split_bf16, weight_planes, rnn_forward,
                       emb_attn_mask, crm_decompress)
 from .pipeline import Separator, GraphedSeparator, PipelinedSeparator, HostPipeline, sm_sharing, mask_loss, pit_mask_loss  # noqa: F401

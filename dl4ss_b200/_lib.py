@@ -54,6 +54,8 @@ SIGNATURES = {
     'dl4ss_premix_fwd': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'dl4ss_premix_shift_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'dl4ss_xcorr_f64': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'dl4ss_conv3x3s2_relu_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    'dl4ss_rowdot_sigmoid_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     'dl4ss_mask_loss_bwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_attn_dot_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     'dl4ss_rnn_bwd_step': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libdl4ss_b200.so')
-SOURCES = ['api.cu', 'stft.cu', 'gemm.cu', 'gemm_tc.cu', 'attn.cu', 'rnn.cu', 'rnn_tc.cu', 'rnn_mma.cu', 'train.cu', 'rnn_bwd.cu', 'xcorr.cu']
+SOURCES = ['api.cu', 'stft.cu', 'gemm.cu', 'gemm_tc.cu', 'attn.cu', 'rnn.cu', 'rnn_tc.cu', 'rnn_mma.cu', 'train.cu', 'rnn_bwd.cu', 'xcorr.cu', 'disc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Wno-deprecated-gpu-targets',
               '--use_fast_math=false', '-Xcompiler', '-fPIC']
 

@@ -470,6 +470,68 @@ class MIX_SPEECH_classifier(nn.Module):
         return _mark_no_autograd(out, self.Linear.weight)
 
 
+class Discriminator(nn.Module):
+    """Discriminator().forward(spec[bs,topk,len,fre]) -> score [bs*topk, 1]: real (clean-source) or predicted spectrogram
+    (TDAA_beta/main_run_sstune_EvalVer.py:328-346): conv 3x3 stride 2 (1->64) + ReLU, twice more (64->64), flatten,
+    Linear(36480 -> 1), sigmoid.  36480 = 64 x 38 x 15 is what a [313,129] spectrogram leaves; other sizes need a matching
+    `final` layer (`flat_features(len, fre)`).  State-dict keys as the reference's: cnn / cnn1 / cnn2 / final.
+    Forward only (dl4ss_conv3x3s2_relu_fwd + dl4ss_rowdot_sigmoid_fwd): the least-squares GAN terms the reference adds
+    with it are `gan_loss_terms`; their gradients are not part of the C ABI (the backward raises, as for every module)."""
+
+    def __init__(self, flat=36480):
+        super(Discriminator, self).__init__()
+        self.cnn = nn.Conv2d(1, 64, (3, 3), stride=(2, 2))
+        self.cnn1 = nn.Conv2d(64, 64, (3, 3), stride=(2, 2))
+        self.cnn2 = nn.Conv2d(64, 64, (3, 3), stride=(2, 2))
+        self.final = nn.Linear(flat, 1)
+
+    @staticmethod
+    def flat_features(length, fre):
+        h, w = length, fre
+        for _ in range(3):
+            h, w = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+        return 64 * h * w
+
+    def forward(self, spec):
+        lib = _lib.load()
+        bs, topk, length, fre = spec.shape
+        x = spec.contiguous().view(bs * topk, 1, length, fre)
+        n = bs * topk
+        for conv in (self.cnn, self.cnn1, self.cnn2):
+            cin, ih, iw = x.shape[1:]
+            oh, ow = (ih - 3) // 2 + 1, (iw - 3) // 2 + 1
+            y = torch.empty(n, conv.out_channels, oh, ow, device=x.device, dtype=torch.float32)
+            rc = lib.dl4ss_conv3x3s2_relu_fwd(_lib.ptr(x, name='spec'), _lib.ptr(conv.weight.detach(), name='weight'),
+                                              _lib.ptr(conv.bias.detach()), _lib.ptr(y), n, cin, ih, iw, conv.out_channels,
+                                              _lib.stream())
+            _lib.check(rc, 'dl4ss_conv3x3s2_relu_fwd')
+            x = y
+        k = x[0].numel()
+        if k != self.final.in_features:
+            raise RuntimeError('size mismatch: the convolutions leave %d features, `final` expects %d' % (k, self.final.in_features))
+        score = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+        rc = lib.dl4ss_rowdot_sigmoid_fwd(_lib.ptr(x), _lib.ptr(self.final.weight.detach(), name='final.weight'),
+                                          _lib.ptr(self.final.bias.detach()), _lib.ptr(score), n, k, _lib.stream())
+        _lib.check(rc, 'dl4ss_rowdot_sigmoid_fwd')
+        return _mark_no_autograd(score, self.final.weight)
+
+
+def gan_loss_terms(score_true, score_false):
+    """The discriminator terms of the reference's training loop (TDAA_beta/main_run_sstune_EvalVer.py:643-652,670-671;
+    `loss_dis_class` is MSELoss, :558): returns a dict of 0-d tensors
+      loss_dis_true  = MSE(score_true, 1)     loss_dis_false = MSE(score_false, 0)     loss_dis = their sum (discriminator step)
+      loss_gen       = MSE(score_false, 1)    (added to the separation loss in the generator step, :670-671)
+      acc_true / acc_false / acc_dis : the accuracies it prints (:645-647)."""
+    st, sf = score_true.detach().float(), score_false.detach().float()
+    t = ((st - 1.0) ** 2).mean()
+    f = (sf ** 2).mean()
+    n = float(st.shape[0])
+    acc_t = (st > 0.5).sum() / n
+    acc_f = (sf < 0.5).sum() / n
+    return {'loss_dis_true': t, 'loss_dis_false': f, 'loss_dis': t + f, 'loss_gen': ((sf - 1.0) ** 2).mean(),
+            'acc_true': acc_t, 'acc_false': acc_f, 'acc_dis': (acc_t + acc_f) / 2}
+
+
 class ATTENTION(nn.Module):
     """ATTENTION(hidden_size, mode='dot'|'align').forward(mix_hidden[N,T,F,E], query[N,E|2E]).
 

@@ -245,6 +245,16 @@ int dl4ss_premix_shift_fwd(const float *src, const int *lengths, const int *shif
 int dl4ss_xcorr_f64(const float *x, const float *y, int B, int Sx, int Sy, int N, int nlags, int lag0,
                     double *out, void *stream);
 
+/* ---- n4: Discriminator forward (replaces cuDNN conv + cuBLAS of TDAA_beta/main_run_sstune_EvalVer.py:328-346) --------
+ * y[n,co,oy,ox] = relu(b[co] + sum_{ci,ky,kx} w[co,ci,ky,kx] * x[n,ci,2*oy+ky,2*ox+kx]): 3x3 kernel, stride 2, no padding,
+ * NCHW fp32, OH = (IH-3)/2+1, OW = (IW-3)/2+1; b may be NULL.  Supported: Cin = 1 (any Cout), or Cin a multiple of 16 with
+ * Cout = 64 and OW <= 32 (the reference's layers: 1->64 on [313,129], 64->64 on [156,64], 64->64 on [77,31]).
+ * N <= 65535 samples per call. */
+int dl4ss_conv3x3s2_relu_fwd(const float *x, const float *w, const float *b, float *y, int N, int Cin, int IH, int IW,
+                             int Cout, void *stream);
+/* out[n] = sigmoid(<x[n, 0:K], w> + b[0]) (the Linear(36480 -> 1) + sigmoid score, :336,345); b may be NULL */
+int dl4ss_rowdot_sigmoid_fwd(const float *x, const float *w, const float *b, float *out, int N, int K, void *stream);
+
 /* ---- training step, backward side -----------------------------------------------------------
  * loss = l0 + 0.5*l1 (real; EvalVer.py:641,659-666) or l_re + l_im (cRM; cRM_EvalVer.py:741-743).
  * dl4ss_mask_loss_bwd: dmask = d(loss)/d(mask), same layout as mask.

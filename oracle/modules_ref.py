@@ -18,6 +18,7 @@ MSELoss) on CPU fp32 (or fp64 when the modules are .double()).
 import numpy as np
 import torch
 from torch import nn
+import torch.nn.functional as F
 
 cRM_k = 10.0      # TDAA_beta/main_run_sstune_cRM_EvalVer.py:28
 cRM_C = 0.1       # TDAA_beta/main_run_sstune_cRM_EvalVer.py:29
@@ -82,6 +83,40 @@ class MIX_SPEECH_classifier(nn.Module):
         x = x.contiguous()
         x = torch.mean(x, 1)
         return torch.sigmoid(self.Linear(x))
+
+
+class Discriminator(nn.Module):
+    """TDAA_beta/main_run_sstune_EvalVer.py:328-346 (the two debugging prints dropped)."""
+
+    def __init__(self, flat=36480):
+        super(Discriminator, self).__init__()
+        self.cnn = nn.Conv2d(1, 64, (3, 3), stride=(2, 2), )
+        self.cnn1 = nn.Conv2d(64, 64, (3, 3), stride=(2, 2), )
+        self.cnn2 = nn.Conv2d(64, 64, (3, 3), stride=(2, 2), )
+        self.final = nn.Linear(flat, 1)
+
+    def forward(self, spec):
+        bs, topk, len, fre = spec.size()
+        spec = spec.view(bs * topk, 1, len, fre)
+        spec = F.relu(self.cnn(spec))
+        spec = F.relu(self.cnn1(spec))
+        spec = F.relu(self.cnn2(spec))
+        spec = spec.view(bs * topk, -1)
+        score = torch.sigmoid(self.final(spec))
+        return score
+
+
+def gan_loss_terms_ref(score_true, score_false):
+    """:643-652 and :670-671 with loss_dis_class = torch.nn.MSELoss() (:558)."""
+    loss_dis_class = torch.nn.MSELoss()
+    n = score_true.size()[0]
+    acc_true = float(torch.sum(score_true > 0.5)) / float(n)
+    acc_false = float(torch.sum(score_false < 0.5)) / float(n)
+    loss_dis_true = loss_dis_class(score_true, torch.ones(n, 1))
+    loss_dis_false = loss_dis_class(score_false, torch.zeros(n, 1))
+    return {'loss_dis_true': loss_dis_true, 'loss_dis_false': loss_dis_false, 'loss_dis': loss_dis_true + loss_dis_false,
+            'loss_gen': loss_dis_class(score_false, torch.ones(n, 1)),
+            'acc_true': acc_true, 'acc_false': acc_false, 'acc_dis': (acc_false + acc_true) / 2}
 
 
 class ATTENTION(nn.Module):

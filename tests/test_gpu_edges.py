@@ -231,3 +231,51 @@ def test_rnn_mma_unsupported_is_loud(cuda):
     x = torch.zeros(16, device=cuda)
     rc = lib.dl4ss_rnn_layer_mma_fwd(L.CELL_LSTM, L.ptr(x), L.ptr(x), None, L.ptr(x), 1, 1, 601, None, None, None, 0, L.stream())
     assert rc != 0 and b'unsupported' in lib.dl4ss_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bs,topk,T,F', [(2, 2, 313, 129), (1, 3, 61, 129), (3, 1, 313, 129)])
+def test_discriminator_matches_oracle(cuda, bs, topk, T, F):
+    """n4: Discriminator forward through the C ABI (direct 3x3 stride-2 convolutions + the 36480-wide score layer) against
+    the oracle's transliteration (TDAA_beta/main_run_sstune_EvalVer.py:328-346) with the same weights, and the
+    least-squares GAN terms of the training loop (:643-652, :670-671)."""
+    import dl4ss_b200 as d
+    from oracle import modules_ref as mr
+    torch.manual_seed(11)
+    flat = d.Discriminator.flat_features(T, F)
+    ref = mr.Discriminator(flat)
+    ours = d.Discriminator(flat)
+    ours.load_state_dict(ref.state_dict())          # same keys: cnn / cnn1 / cnn2 / final
+    ours = ours.to(cuda)
+    true_map = torch.rand(bs, topk, T, F) * 2.0
+    false_map = torch.rand(bs, topk, T, F)
+    with torch.no_grad():
+        r_true, r_false = ref(true_map), ref(false_map)
+        o_true, o_false = ours(true_map.to(cuda)), ours(false_map.to(cuda))
+    assert o_true.shape == (bs * topk, 1)
+    assert (o_true.cpu() - r_true).abs().max().item() < 1e-5
+    assert (o_false.cpu() - r_false).abs().max().item() < 1e-5
+    lr, lo = mr.gan_loss_terms_ref(r_true, r_false), d.gan_loss_terms(o_true, o_false)
+    for k in lr:
+        assert abs(float(lo[k]) - float(lr[k])) < 1e-5, k
+    # the intermediate activations as well: first two layers against torch's convolution
+    import torch.nn.functional as Fn
+    x = true_map.view(bs * topk, 1, T, F)
+    a1 = Fn.relu(ref.cnn(x))
+    lib = d.load_library()
+    from dl4ss_b200 import _lib
+    y1 = torch.empty(a1.shape, device=cuda)
+    rc = lib.dl4ss_conv3x3s2_relu_fwd(_lib.ptr(x.to(cuda).contiguous()), _lib.ptr(ours.cnn.weight.detach()),
+                                      _lib.ptr(ours.cnn.bias.detach()), _lib.ptr(y1), bs * topk, 1, T, F, 64, _lib.stream())
+    assert rc == 0
+    assert (y1.cpu() - a1.detach()).abs().max().item() < 1e-5
+    a2 = Fn.relu(ref.cnn1(a1))
+    y2 = torch.empty(a2.shape, device=cuda)
+    rc = lib.dl4ss_conv3x3s2_relu_fwd(_lib.ptr(y1), _lib.ptr(ours.cnn1.weight.detach()), _lib.ptr(ours.cnn1.bias.detach()),
+                                      _lib.ptr(y2), bs * topk, 64, a1.shape[2], a1.shape[3], 64, _lib.stream())
+    assert rc == 0
+    assert (y2.cpu() - a2.detach()).abs().max().item() < 2e-5 * max(1.0, a2.abs().max().item())
+    with pytest.raises(RuntimeError):               # an unsupported layer shape is an error, not a fallback
+        rc = lib.dl4ss_conv3x3s2_relu_fwd(_lib.ptr(y1), _lib.ptr(ours.cnn1.weight.detach()), None, _lib.ptr(y2),
+                                          bs * topk, 24, 10, 10, 64, _lib.stream())
+        _lib.check(rc, 'dl4ss_conv3x3s2_relu_fwd')

@@ -197,3 +197,21 @@ def test_synth_batch_is_reference_shaped():
     assert np.allclose(peak, 10 ** (b['gains_db'] / 20.0))
     b2 = synth.make_batch(3, 8000, 2, seed=5, active_len=(3000, 8000))
     assert np.array_equal(b['mix_wav'], b2['mix_wav'])
+
+
+def test_discriminator_oracle_shape_constant_and_losses():
+    """The reference's own shape constant: Linear(36480, 1) after three 3x3/stride-2 convolutions of a [313,129]
+    spectrogram (TDAA_beta/main_run_sstune_EvalVer.py:334), and the least-squares GAN terms of :643-652,670."""
+    import dl4ss_b200.modules as M
+    assert M.Discriminator.flat_features(313, 129) == 36480
+    torch.manual_seed(3)
+    dis = mr.Discriminator()
+    with torch.no_grad():
+        s_true = dis(torch.rand(2, 2, 313, 129))
+        s_false = dis(torch.rand(2, 2, 313, 129) * 0.5)
+    assert s_true.shape == (4, 1) and float(s_true.min()) > 0 and float(s_true.max()) < 1
+    ref = mr.gan_loss_terms_ref(s_true, s_false)
+    ours = M.gan_loss_terms(s_true, s_false)          # pure tensor arithmetic: runs on the CPU too
+    for k in ('loss_dis_true', 'loss_dis_false', 'loss_dis', 'loss_gen', 'acc_true', 'acc_false', 'acc_dis'):
+        assert abs(float(ours[k]) - float(ref[k])) < 1e-6, k
+    assert abs(float(ref['loss_dis']) - float(((s_true - 1) ** 2).mean() + (s_false ** 2).mean())) < 1e-7
