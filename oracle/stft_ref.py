@@ -10,8 +10,10 @@ Algorithm restated (published librosa.core.spectrum behaviour):
   istft: per frame Hermitian-extend, ifft().real, x window, overlap-add into a float32 buffer,
          divide by the window sum-square where > tiny(float32), trim n_fft/2 both sides,
          length hop*(T-1).
-Parity unpinned against librosa values (library absent); pinned against torch.stft/istft and
-scipy in tests/test_oracle_stft.py.
+Pinned: against outputs of the reference's own numpy stft / istft (Cocktail/software/DL4SS_Keras/
+test_stft_istft.py:9-63 -> tests/golden/ref_stft_*.npz, tests/test_oracle_refpin.py; `center=False` is
+the restatement of those functions) and against torch.stft/istft + scipy (tests/test_oracle.py).
+librosa itself is absent from the image: its values are not compared directly.
 """
 import numpy as np
 
