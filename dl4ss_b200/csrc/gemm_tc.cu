@@ -28,6 +28,7 @@ constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;     // 96 KB
 constexpr int TC_EPI_WARPS = 20;                              // up to 5 per TMEM sub-partition (EpiTraits<>::PARTS of them work)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_STAGE_PITCH = 33;                            // floats per row of a warp's 32x32 store-transpose tile
+constexpr int TC_RING = 4;                                    // work-item ring slots (power of two)
 constexpr int TC_STORE_WARPS = 8;                             // warps of the plain epilogue (4 sub-partitions x 2 parts)
 constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                            (size_t)TC_STORE_WARPS * 32 * TC_STAGE_PITCH * sizeof(float);
@@ -251,13 +252,18 @@ __device__ __forceinline__ const EpiAttn &epi_of_split(const EpiAttn &e, int) { 
 template <typename Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int M, int N, int kblocks, int m_tiles, int n_tiles, int nsplit, const Epi epi) {
+                   int M, int N, int kblocks, int m_tiles, int n_tiles, int nsplit, unsigned *sched, const Epi epi) {
     constexpr int NSTEP = EpiTraits<Epi>::NSTEP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)TSTAGES * TSTAGE_BYTES);
     uint64_t *full = bars, *empty = bars + TSTAGES, *tfull = bars + 2 * TSTAGES, *tempty = bars + 2 * TSTAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TSTAGES + 4);
+    // work-item ring: the producer lane publishes the item ids (dynamic: taken from the launch's global counter, so CTAs
+    // that become resident late -- next to another stream's recurrent launch -- simply find less work; static: blockIdx +
+    // k * gridDim), the MMA lane and the epilogue warps consume them in the same order
+    uint64_t *sfull = bars + 2 * TSTAGES + 5, *sempty = sfull + TC_RING;
+    volatile int *sched_w = reinterpret_cast<volatile int *>(sempty + TC_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_work = m_tiles * n_tiles * nsplit;
@@ -268,6 +274,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EpiTraits<Epi>::PARTS); }
+        for (int r = 0; r < TC_RING; ++r) { mbar_init(&sfull[r], 1); mbar_init(&sempty[r], 1 + 4 * EpiTraits<Epi>::PARTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -282,10 +289,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int w = sched ? (int)atomicAdd(sched, 1u) : (int)blockIdx.x;
+            for (int it = 0;; ++it) {
+                const int slot = it & (TC_RING - 1);
+                mbar_wait(&sempty[slot], (((uint32_t)it / TC_RING) & 1u) ^ 1u);
+                const bool live = w < total_work;
+                sched_w[slot] = live ? w : -1;
+                mbar_arrive(&sfull[slot]);
+                if (!live) break;
+                const int wnext = sched ? (int)atomicAdd(sched, 1u) : w + (int)gridDim.x;     // in flight while this item's k-blocks load
                 const int tile = (nsplit == 1) ? w : w / nsplit, ks = w - tile * nsplit;
                 const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
                 const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
+                w = wnext;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *st = tiles + (size_t)stage * TSTAGE_BYTES;
@@ -302,7 +318,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (lane == 0) {
                         constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int it = 0;; ++it) {
+                const int slot = it & (TC_RING - 1);
+                mbar_wait(&sfull[slot], ((uint32_t)it / TC_RING) & 1u);
+                const int w = sched_w[slot];
+                mbar_arrive(&sempty[slot]);
+                if (w < 0) break;
                 const int ks = (nsplit == 1) ? 0 : w % nsplit;
                 const int kb0 = ks * kper, kb1 = min(kb0 + kper, kblocks);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -334,7 +355,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float *stage = reinterpret_cast<float *>(tiles + (size_t)TSTAGES * TSTAGE_BYTES + 256) +
                        (size_t)((part * 4 + quarter) % TC_STORE_WARPS) * 32 * TC_STAGE_PITCH;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int it = 0;; ++it) {
+            const int slot = it & (TC_RING - 1);
+            mbar_wait(&sfull[slot], ((uint32_t)it / TC_RING) & 1u);
+            const int w = sched_w[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[slot]);
+            if (w < 0) break;
             const int tile = (nsplit == 1) ? w : w / nsplit, ks = w - tile * nsplit;
             const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * NSTEP;
             mbar_wait(&tfull[acc], acc_phase);
@@ -354,9 +381,52 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+    if (sched != nullptr && threadIdx.x == 0) {      // the last CTA out re-arms the launch's counter pair (graph replays reuse it)
+        if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
+// Counter pairs {next item, CTAs finished} of the dynamically scheduled launches, zeroed once; a launch takes one pair,
+// its last CTA re-zeroes it.  Eager launches cycle through a ring (far longer than any launch queue); launches recorded
+// into a CUDA graph keep their pair for the graph's life (replays of a node never overlap themselves), so those come
+// from a second region that is handed out once -- when it is used up, further captured launches fall back to the static
+// schedule (sched == nullptr).
+constexpr unsigned SCHED_EAGER = 4096, SCHED_GRAPH = 8192;
+struct SchedPool {
+    std::mutex mu;
+    unsigned *base = nullptr;
+    unsigned eager = 0, graph = 0;
+};
+static SchedPool g_sched[DL4SS_MAX_DEVICES];
+static bool g_dynamic = [] { const char *e = getenv("DL4SS_GEMM_DYNAMIC"); return !(e && e[0] == '0'); }();
+
+static unsigned *sched_pair(cudaStream_t st) {
+    if (!g_dynamic) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DL4SS_MAX_DEVICES) return nullptr;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    SchedPool &p = g_sched[dev];
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (p.base == nullptr) {
+        if (cs != cudaStreamCaptureStatusNone) return nullptr;          // no allocation while a capture is open
+        const size_t bytes = (size_t)2 * (SCHED_EAGER + SCHED_GRAPH) * sizeof(unsigned);
+        unsigned *b = nullptr;
+        if (cudaMalloc(&b, bytes) != cudaSuccess || cudaMemset(b, 0, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        p.base = b;
+    }
+    if (cs != cudaStreamCaptureStatusNone) {
+        if (p.graph >= SCHED_GRAPH) return nullptr;
+        return p.base + 2 * (size_t)(SCHED_EAGER + p.graph++);
+    }
+    return p.base + 2 * (size_t)(p.eager++ % SCHED_EAGER);
+}
+
 EncodeTiledFn tensor_map_encoder() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
@@ -434,7 +504,7 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
     if (total < grid) grid = (int)total;
     auto kern = gemm_bf16x3_kernel<Epi>;
     DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, nsplit, epi);
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, nsplit, sched_pair(st), epi);
     DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel");
     return DL4SS_OK;
 }

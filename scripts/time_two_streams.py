@@ -49,9 +49,9 @@ run(1, 0, 0)
 run(1, 0, 0, 512)
 run(2, 0, 0)
 run(2, 3, 0)
+run(2, 3, 120)
 run(2, 3, 88)
-run(2, 3, 74)
-run(2, 2, 68)
-run(3, 3, 88)
+run(2, 2, 0)
+run(3, 3, 0)
 lib.dl4ss_rnn_tc_set_tiles_per_cta(0)
 lib.dl4ss_gemm_tc_set_max_ctas(0)
