@@ -227,7 +227,7 @@ rnn_bwd_kernel(const RnnBwdParams p) {
             __syncthreads();
             bw_stamp(p, s, 6);
             if (tid == 0) {
-                __threadfence();
+                // release = MEMBAR.GPU + RED, cumulative over the barrier above: a separate __threadfence() paid a second membar
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
             }
             bw_stamp(p, s, 7);
@@ -463,7 +463,7 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
             __syncthreads();
             bm_stamp(p, s, 6);
             if (tid == 0) {
-                __threadfence();
+                // release = MEMBAR.GPU + RED, cumulative over the barrier above: a separate __threadfence() paid a second membar
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
             }
             bm_stamp(p, s, 7);

@@ -171,7 +171,6 @@ rnn_mma_kernel(const RnnMmaParams p) {
                 mbar_wait(&rel[grp], ph); ph ^= 1;
                 if (lane == 0) {
                     mbar_arrive(&reldone[grp]);
-                    __threadfence();
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n"
                                  ::"l"(counters + (size_t)tau * MM_CTR_STRIDE), "r"(1u) : "memory");
                 }

@@ -137,6 +137,12 @@ class sm_sharing(object):
     geometry it was captured with); (0, 0) = a lone batch owns the GPU."""
     PIPELINED = (3, 88)
 
+    @staticmethod
+    def for_batch(B, inflight):
+        """Geometry for `inflight` batches of B utterances: the shared form while two recurrent launches fit side by side
+        (B <= 288: 3 tile groups x 2 directions x 10 slices = 60 CTAs each), otherwise every launch takes what it needs."""
+        return sm_sharing.PIPELINED if (inflight > 1 and B <= 288) else None
+
     def __init__(self, tiles, gemm_ctas):
         self.want = (int(tiles), int(gemm_ctas))
 
@@ -233,7 +239,7 @@ class PipelinedSeparator(object):
     def __init__(self, separator, B, L, S, depth=2, device=None, wav_dtype=torch.float32):
         dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.dev, self.depth = dev, depth
-        share = sm_sharing.PIPELINED if depth > 1 else None
+        share = sm_sharing.for_batch(B, depth)
         self.gs = [GraphedSeparator(separator, B, L, S, wav_dtype, dev, share=share) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
@@ -288,10 +294,10 @@ class HostPipeline(object):
         self.depth = depth
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         # with graphs every slot computes on its own stream with the shared-SM launch geometry: two batches in flight
-        share = sm_sharing.PIPELINED if (graphs and depth > 1 and concurrent) else None
+        share = sm_sharing.for_batch(B, depth) if (graphs and concurrent) else None
         # two compute streams whatever the depth: a third recurrent launch would not fit next to two (3 x 60 CTAs) and its
         # half-placed groups would spin on SMs the projections need; further slots only decouple the copies
-        self.s_cmp = [torch.cuda.Stream(dev) for _ in range(2)] if share else None
+        self.s_cmp = [torch.cuda.Stream(dev) for _ in range(2)] if (graphs and concurrent and depth > 1) else None
         self.gs = [GraphedSeparator(separator, B, L, S, device=dev, share=share) for _ in range(depth)] if graphs else None
         if graphs:
             self.d_wav = [g.wav for g in self.gs]
