@@ -343,7 +343,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                     }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xempty[tl * 2 + buf]);
-                if (tr && lane == 0) stamp(p, s, 12);
+                if (tr && lane == 0) stamp(p, s, 15);
 
                 float hnew[4], gv[4][G], aux[4];
 #pragma unroll
@@ -396,8 +396,11 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                     // warp waits for them; its MEMBAR.GPU + RED then covers their stores (cumulativity through the barrier).
                     // 8 x fewer atomics on the group's counter line, which serialise at ~27 cycles each in L2
                     if (releaser) {
+                        const bool trr = (blockIdx.x == 0 && tl == 0);
+                        if (trr && lane == 0) stamp(p, s, 12);
                         asm volatile("bar.sync %0, %1;\n" ::"r"(1 + tl), "n"(RT_EPI_PER_TILE * 32) : "memory");
                         if (lane == 0) {
+                            const bool tr = trr;
                             if (tr) stamp(p, s, 13);
                             asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
                             if (tr) stamp(p, s, 14);

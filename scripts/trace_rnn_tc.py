@@ -26,7 +26,7 @@ with torch.no_grad():
     lib.dl4ss_rnn_tc_set_trace(None, 0)
 t = buf.cpu().numpy().reshape(steps, 16)
 names = ['poll_start', 'poll_done', 'tma_issued', 'h0_landed', 'hlast_landed', 'mma_committed', 'tfull_seen', 'tmem_read',
-         'transposed', 'math_done', 'stores_done', 'xfull_seen', 'x_read', 'threadfence', 'red_done', 'unused']
+         'transposed', 'math_done', 'stores_done', 'xfull_seen', 'rel_at_barrier', 'rel_barrier_done', 'red_done', 'x_read']
 print('step-to-step (poll_done) cycles:', np.diff(t[10:60, 1]).mean())
 base = t[10:60, 1:2]
 rel = (t[10:60, :16] - base).astype(np.float64)
