@@ -507,3 +507,64 @@ def test_modules_backward_is_loud(cuda):
     with torch.no_grad():
         out2, hid2 = ours['mix'](feas)
     assert not hid2.requires_grad and torch.equal(hid2, hid.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cell,H,B,T,tiles', [('lstm', 300, 200, 9, 3), ('gru', 300, 97, 11, 2), ('lstm', 100, 40, 13, 0),
+                                              ('gru', 36, 33, 7, 3), ('lstm', 320, 70, 6, 1)])
+def test_rnn_tc_tiles_per_cta_and_partial_slices(cuda, cell, H, B, T, tiles):
+    """The round-2 recurrent kernel in every geometry: 1 / 2 / 3 utterance tiles per CTA (dl4ss_rnn_tc_set_tiles_per_cta),
+    hidden sizes whose last 32-unit slice is partial (300 -> 12 units, 100 -> 4, 36 -> 4) or absent (320), batches with a
+    partial last tile -- against nn.LSTM / nn.GRU on the CPU, and identical across geometries."""
+    import dl4ss_b200 as d
+    from dl4ss_b200 import _lib
+    lib = _lib.load()
+    ref, ours = build_pair(cell, 2, 129, T, False, H=H)
+    try:
+        assert lib.dl4ss_rnn_tc_supported(H, _lib.CELL_LSTM if cell == 'lstm' else _lib.CELL_GRU)
+        torch.manual_seed(9)
+        x = torch.rand(B, T, 129) * 2
+        with torch.no_grad():
+            y_ref, _ = ref['mix'].layer(x)
+            lib.dl4ss_rnn_tc_set_tiles_per_cta(tiles)
+            y = ours['mix'].encode(x.to(cuda)).cpu()
+            lib.dl4ss_rnn_tc_set_tiles_per_cta(0)
+            y0 = ours['mix'].encode(x.to(cuda)).cpu()
+        assert tuple(y.shape) == (B, T, 2 * H)
+        assert (y - y_ref).abs().max().item() < 2e-5
+        assert torch.equal(y, y0)          # the geometry only moves work between CTAs
+    finally:
+        lib.dl4ss_rnn_tc_set_tiles_per_cta(0)
+        d.config.HIDDEN_UNITS = 300
+
+
+@pytest.mark.gpu
+def test_pipelined_separator_equals_eager(cuda):
+    """Two batches in flight on two streams (PipelinedSeparator, the shared-SM launch geometry, dynamically scheduled
+    projections): every result equals the eager single-stream call bit for bit, in submission order, slot reuse included."""
+    import dl4ss_b200 as d
+    B, L, S = 40, 8000, 2
+    _, ours = build_pair('lstm', 2, 129, 63, False)
+    sep = d.Separator(ours['mix'], ours['emb'], ours['att'], ours['adj'])
+    g = torch.Generator(device='cuda').manual_seed(6)
+    wavs = [torch.randn(B, L, device=cuda, generator=g) * 0.3 for _ in range(5)]
+    idxs = [torch.sort(torch.stack([torch.randperm(101)[:S] for _ in range(B)]), 1)[0].to(cuda) for _ in range(5)]
+    eager = [sep.separate(w, i).clone() for w, i in zip(wavs, idxs)]
+    assert d.sm_sharing.for_batch(B, 2) == d.sm_sharing.PIPELINED and d.sm_sharing.for_batch(512, 2) is None
+    pipe = d.PipelinedSeparator(sep, B, L, S, depth=2)
+    got, pending = [], []
+    for w, i in zip(wavs, idxs):
+        pending.append(pipe.submit(w, i))
+        if len(pending) == 2:
+            k = pending.pop(0)
+            got.append(pipe.result(k).clone())
+            pipe.release(k)
+    while pending:
+        k = pending.pop(0)
+        got.append(pipe.result(k).clone())
+        pipe.release(k)
+    torch.cuda.synchronize()
+    for a, e in zip(got, eager):
+        assert torch.equal(a, e)
+    # the geometry knobs are restored after every capture: an eager call afterwards is the lone-batch form again
+    assert torch.equal(sep.separate(wavs[0], idxs[0]), eager[0])
