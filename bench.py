@@ -541,7 +541,7 @@ def training_extra(device, B=256, steps=5, warmup=3, dist=None, rank=0, world=1,
         small = training_extra(device, 64, 3, warmup, dist, rank, world, brief=True)
         out['at_64_utterances_per_gpu'] = {'ms_per_step': small['ms_per_step'], 'value': small['value'], 'unit': 'audio-s/s'}
         out['batch_note'] = ('256 utterances per GPU, the inference batch: the forward recurrence serves them in one launch per layer, '
-                             'the BPTT kernel walks them in chunks of 64')
+                             'the BPTT kernel walks four 16-utterance tiles per CTA in one launch per layer')
     return out
 
 

@@ -20,6 +20,7 @@
 //   * siblings of a (direction, tile) group synchronise through one L2 counter (release / acquire); groups never wait
 //     on each other; the launch is cooperative so the waits cannot deadlock.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace dl4ss {
 
@@ -250,9 +251,22 @@ rnn_bwd_kernel(const RnnBwdParams p) {
 //     mbarrier, two issued by lane 0 of every warp once thread 0 has seen the group counter (the lanes of one warp would
 //     issue them one after the other through the uniform datapath): no per-thread cp.async, no wait_group + CTA barrier;
 //   * row pitch == 4 (mod 32) 32-bit words: the 8 rows x 4 k-pairs of a fragment load hit 32 different banks.
+//   * up to BM_MAXT utterance tiles per CTA (round 2): 64 utterances fill the 120 co-resident CTAs with one tile each; a larger
+//     batch used to run in chunks of 64, one launch after the other, each a pure latency chain.  Now a CTA walks its tiles
+//     in turn inside every step, with the same resident W_hh^T slice and the same tile buffer: while tile i's gradients
+//     travel to its siblings (release -> counter visible -> bulk load: ~4 k of the 7.5 k cycles of a step) the CTA works
+//     on tile i+1.  The six warps that own no cells look at the NEXT tile's counter during the product and, when its
+//     siblings have published (normal from 2 tiles per CTA on), request its rows right after the product, under this
+//     tile's gate arithmetic; the release (MEMBAR.GPU + RED, ~1.3 k cycles) is issued by one of those warps, so it stalls
+//     no owner.  256 utterances: 3.30 ms per layer in one launch against 4 x 1.31 ms (5.2 k instead of 7.45 k cycles per
+//     tile and step).
 constexpr int BM_NW = 16;
 constexpr int BM_THREADS = 32 * BM_NW;
 constexpr int BM_NP = 24;                 // units padded to 3 n-tiles of 8
+constexpr int BM_FREE0 = 10;              // warps [10, 16) hold no cell owners (BW_CELLS = 320 = 10 warps)
+constexpr int BM_MAXT = 4;                // utterance tiles per CTA: while one tile's gate gradients travel to its siblings
+                                          // (release -> counter visible -> bulk load: ~4 k of the 7.5 k cycles of a step) the CTA
+                                          // works on the next tile with the same resident W_hh^T slice and the same tile buffer
 
 struct RnnBwdTcParams {
     const float *dy, *whh, *gates, *cells, *y;
@@ -261,6 +275,7 @@ struct RnnBwdTcParams {
     unsigned *counters;
     int B, T, H, GHg, pitch, nks;
     int b_begin, batch_tiles, nslices;
+    int tpc, ngroups;       // utterance tiles a CTA walks per step (<= BM_MAXT), groups of tpc tiles in this launch
     long long *trace;
     int trace_steps;
 };
@@ -293,12 +308,11 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int bid = blockIdx.x;
     const int slice = bid % p.nslices; bid /= p.nslices;
-    const int bt = bid % p.batch_tiles;
-    const int dir = bid / p.batch_tiles;
-    const int row0 = p.b_begin + bt * BW_BT;
-    const int nrows = min(BW_BT, p.B - row0);
+    const int grp = bid % p.ngroups;
+    const int dir = bid / p.ngroups;
+    const int bt0 = grp * p.tpc;
+    const int nt = min(p.tpc, p.batch_tiles - bt0);          // tiles this CTA walks
     const int u0 = slice * BW_HS;
-    unsigned *counter = p.counters + (size_t)(dir * p.batch_tiles + bt) * BW_CTR_STRIDE;
     const size_t plane_elems = (size_t)p.B * T * 2 * GHg;
 
     {   // zero both operand arrays (pad rows / columns / absent utterances stay zero), then the resident W planes
@@ -328,13 +342,16 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
     const uint32_t *A32 = reinterpret_cast<const uint32_t *>(dgA);
     const uint32_t *W32 = reinterpret_cast<const uint32_t *>(Wt);
     const int pw = pitch >> 1;                                   // row pitch in 32-bit words
-    // owner mapping: thread -> cell (r, j)
+    // owner mapping: thread -> cell (r, j) of every tile
     const bool owner = tid < BW_CELLS;
     const int orow = tid / BW_HS, oj = tid - orow * BW_HS;
-    const int ob = row0 + orow;
-    const bool oval = owner && ob < p.B;
     const int ou = u0 + oj;
-    float carry = 0.f;
+    float carry[BM_MAXT];
+#pragma unroll
+    for (int i = 0; i < BM_MAXT; ++i) carry[i] = 0.f;
+    uint32_t uses0 = 0, uses1 = 0;                               // completed uses of the two mbarriers (phase parity)
+    bool early = false;                                          // this tile's rows were requested during the previous tile
+    volatile int *early_flag = reinterpret_cast<volatile int *>(bar + 2);
 
     for (int s = 0; s < T; ++s) {
         const int t = dir ? s : (T - 1 - s);
@@ -342,142 +359,195 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
         const int tl = dir ? t - 1 : t + 1;
         const bool has_prev = (tp >= 0 && tp < T);
 
-        float dyv = 0.f, gv[G], cv = 0.f, pv = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) gv[g] = 0.f;
-        const size_t row = ((size_t)ob * T + t) * 2 + dir;
-        if (oval) {
-            dyv = __ldg(p.dy + ((size_t)ob * T + t) * 2 * H + (size_t)dir * H + ou);
-#pragma unroll
-            for (int g = 0; g < G; ++g) gv[g] = __ldg(p.gates + row * GH + (size_t)g * H + ou);
-            cv = __ldg(p.cells + row * H + ou);
-            if (has_prev) {
-                if (CELL == DL4SS_CELL_LSTM) pv = __ldg(p.cells + (((size_t)ob * T + tp) * 2 + dir) * H + ou);
-                else pv = __ldg(p.y + ((size_t)ob * T + tp) * 2 * H + (size_t)dir * H + ou);
-            }
-        }
+        for (int ti = 0; ti < BM_MAXT; ++ti) {
+            if (ti < nt) {
+                const int row0 = p.b_begin + (bt0 + ti) * BW_BT;
+                const int nrows = min(BW_BT, p.B - row0);
+                unsigned *counter = p.counters + (size_t)(dir * p.batch_tiles + bt0 + ti) * BW_CTR_STRIDE;
+                const int ob = row0 + orow;
+                const bool oval = owner && ob < p.B;
+                const bool tr0 = (ti == 0);
 
-        float dh = dyv;
-        if (s > 0) {
-            // thread 0 watches the group counter; the tile's 32 row copies are then issued by lane 0 of every warp (two
-            // each): 32 copies from the lanes of ONE warp leave through the uniform datapath one after the other (~1 k cycles)
-            if (tid == 0) {
-                bm_stamp(p, s, 0);
-                const unsigned want = (unsigned)p.nslices * (unsigned)s;
-                while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
-                mbar_expect_tx(&bar[0], (uint32_t)(nrows * 2 * GHg * 2));
-                mbar_arrive(&bar[1]);
-                bm_stamp(p, s, 1);
-            }
-            mbar_wait(&bar[1], (uint32_t)(s - 1) & 1u);
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.global;\n" ::: "memory");   // the siblings' generic stores -> bulk-copy reads
+                float dyv = 0.f, gv[G], cv = 0.f, pv = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32 / BM_NW; ++i) {
-                    const int idx = warp * (32 / BM_NW) + i;
-                    const int r = idx >> 1, pl = idx & 1;
-                    if (r < nrows)
-                        bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
-                                 p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0 + r) * T + tl) * 2 + dir) * GHg,
-                                 (uint32_t)(GHg * 2), &bar[0]);
+                for (int g = 0; g < G; ++g) gv[g] = 0.f;
+                const size_t row = ((size_t)ob * T + t) * 2 + dir;
+                if (oval) {
+                    dyv = __ldg(p.dy + ((size_t)ob * T + t) * 2 * H + (size_t)dir * H + ou);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) gv[g] = __ldg(p.gates + row * GH + (size_t)g * H + ou);
+                    cv = __ldg(p.cells + row * H + ou);
+                    if (has_prev) {
+                        if (CELL == DL4SS_CELL_LSTM) pv = __ldg(p.cells + (((size_t)ob * T + tp) * 2 + dir) * H + ou);
+                        else pv = __ldg(p.y + ((size_t)ob * T + tp) * 2 * H + (size_t)dir * H + ou);
+                    }
                 }
-            }
-            mbar_wait(&bar[0], (uint32_t)(s - 1) & 1u);
-            bm_stamp(p, s, 2);
 
-            float acc[3][4];
+                // the (tile, step) that follows this one in the CTA's walk, and whether it reads exchanged rows
+                const bool last_ti = (ti + 1 >= nt);
+                const int s_n = last_ti ? s + 1 : s;
+                const int ti_n = last_ti ? 0 : ti + 1;
+                const bool have_next = (s_n >= 1 && s_n < T);
+                const int row0_n = p.b_begin + (bt0 + ti_n) * BW_BT;
+                const int nrows_n = min(BW_BT, p.B - row0_n);
+                const int t_n = dir ? s_n : (T - 1 - s_n);
+                const int tl_n = dir ? t_n - 1 : t_n + 1;
+                const unsigned *counter_n = p.counters + (size_t)(dir * p.batch_tiles + bt0 + ti_n) * BW_CTR_STRIDE;
+
+                float dh = dyv;
+                unsigned seen_n = 0;
+                if (s > 0) {
+                    if (!early) {
+                        // thread 0 watches the tile's group counter; the 32 row copies are then issued by lane 0 of every warp (two
+                        // each): 32 copies from the lanes of ONE warp leave through the uniform datapath one after the other (~1 k cycles)
+                        if (tid == 0) {
+                            if (tr0) bm_stamp(p, s, 0);
+                            const unsigned want = (unsigned)p.nslices * (unsigned)s;
+                            while (bw_ld_acquire(counter) < want) { __nanosleep(20); }
+                            mbar_expect_tx(&bar[0], (uint32_t)(nrows * 2 * GHg * 2));
+                            mbar_arrive(&bar[1]);
+                            if (tr0) bm_stamp(p, s, 1);
+                        }
+                        mbar_wait(&bar[1], uses1 & 1u);
+                        ++uses1;
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.global;\n" ::: "memory");   // the siblings' generic stores -> bulk-copy reads
 #pragma unroll
-            for (int n = 0; n < 3; ++n)
+                            for (int i = 0; i < 32 / BM_NW; ++i) {
+                                const int idx = warp * (32 / BM_NW) + i;
+                                const int r = idx >> 1, pl = idx & 1;
+                                if (r < nrows)
+                                    bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
+                                             p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0 + r) * T + tl) * 2 + dir) * GHg,
+                                             (uint32_t)(GHg * 2), &bar[0]);
+                            }
+                        }
+                    }
+                    mbar_wait(&bar[0], uses0 & 1u);
+                    ++uses0;
+                    if (tr0) bm_stamp(p, s, 2);
+                    // one look at the NEXT tile's counter, in flight during the product (warp 15 holds no cell owners)
+                    if (warp == BM_NW - 1 && lane == 0 && have_next) seen_n = bw_ld_acquire(counter_n);
+
+                    float acc[3][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-            for (int ks = warp; ks < p.nks; ks += BM_NW) {
-                const int kw = ks * 8 + ft;                          // word index of k = 16*ks + 2*ft
-                uint32_t ah[4], al[4];
-                const uint32_t *a0 = A32 + (size_t)fg * pw + kw;
-                const uint32_t *a1 = a0 + (size_t)BW_BT * pw;        // lo plane
-                ah[0] = a0[0]; ah[1] = a0[8 * pw]; ah[2] = a0[4]; ah[3] = a0[8 * pw + 4];
-                al[0] = a1[0]; al[1] = a1[8 * pw]; al[2] = a1[4]; al[3] = a1[8 * pw + 4];
+                    for (int n = 0; n < 3; ++n)
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    const uint32_t *b0 = W32 + (size_t)(8 * n + fg) * pw + kw;
-                    const uint32_t *b1 = b0 + (size_t)BM_NP * pw;    // lo plane
-                    const uint32_t bh0 = b0[0], bh1 = b0[4], bl0 = b1[0], bl1 = b1[4];
-                    mma_bf16_16816(acc[n], ah, bl0, bl1);
-                    mma_bf16_16816(acc[n], al, bh0, bh1);
-                    mma_bf16_16816(acc[n], ah, bh0, bh1);
+                        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+                    for (int ks = warp; ks < p.nks; ks += BM_NW) {
+                        const int kw = ks * 8 + ft;                          // word index of k = 16*ks + 2*ft
+                        uint32_t ah[4], al[4];
+                        const uint32_t *a0 = A32 + (size_t)fg * pw + kw;
+                        const uint32_t *a1 = a0 + (size_t)BW_BT * pw;        // lo plane
+                        ah[0] = a0[0]; ah[1] = a0[8 * pw]; ah[2] = a0[4]; ah[3] = a0[8 * pw + 4];
+                        al[0] = a1[0]; al[1] = a1[8 * pw]; al[2] = a1[4]; al[3] = a1[8 * pw + 4];
+#pragma unroll
+                        for (int n = 0; n < 3; ++n) {
+                            const uint32_t *b0 = W32 + (size_t)(8 * n + fg) * pw + kw;
+                            const uint32_t *b1 = b0 + (size_t)BM_NP * pw;    // lo plane
+                            const uint32_t bh0 = b0[0], bh1 = b0[4], bl0 = b1[0], bl1 = b1[4];
+                            mma_bf16_16816(acc[n], ah, bl0, bl1);
+                            mma_bf16_16816(acc[n], al, bh0, bh1);
+                            mma_bf16_16816(acc[n], ah, bh0, bh1);
+                        }
+                    }
+                    float *pwarp = part + (size_t)warp * (BW_BT * BM_NP);
+#pragma unroll
+                    for (int n = 0; n < 3; ++n) {
+                        *reinterpret_cast<float2 *>(pwarp + fg * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][0], acc[n][1]);
+                        *reinterpret_cast<float2 *>(pwarp + (fg + 8) * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][2], acc[n][3]);
+                    }
+                    if (tr0) bm_stamp(p, s, 3);
+                    __syncthreads();
+                    if (tr0) bm_stamp(p, s, 4);
+                    // the tile buffer is free: if the next tile's siblings have published, request its rows now, under the gate
+                    // arithmetic of this tile (with >= 2 tiles per CTA they normally have: their release is a whole tile old)
+                    // (the six warps without cell owners share the 32 copies: one warp's lanes would issue them one after the other)
+                    if (warp >= BM_FREE0) {
+                        if (warp == BM_NW - 1 && lane == 0) {
+                            const bool rdy = have_next && seen_n >= (unsigned)p.nslices * (unsigned)s_n;
+                            if (rdy) mbar_expect_tx(&bar[0], (uint32_t)(nrows_n * 2 * GHg * 2));
+                            *early_flag = rdy ? 1 : 0;
+                        }
+                        asm volatile("bar.sync 1, %0;\n" ::"n"(32 * (BM_NW - BM_FREE0)) : "memory");
+                        if (*early_flag != 0 && lane < 6) {
+                            const int idx = (warp - BM_FREE0) * 6 + lane;            // 36 slots for 32 copies
+                            const int r = idx >> 1, pl = idx & 1;
+                            if (idx < 32 && r < nrows_n) {
+                                asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                                bulk_g2s(dgA + (size_t)(pl * BW_BT + r) * pitch,
+                                         p.xplanes + (size_t)pl * plane_elems + (((size_t)(row0_n + r) * T + tl_n) * 2 + dir) * GHg,
+                                         (uint32_t)(GHg * 2), &bar[0]);
+                            }
+                        }
+                    }
+                    if (owner) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int w = 0; w < BM_NW; ++w) v += part[w * (BW_BT * BM_NP) + orow * BM_NP + oj];
+                        dh += v;
+                    }
                 }
-            }
-            float *pwarp = part + (size_t)warp * (BW_BT * BM_NP);
-#pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                *reinterpret_cast<float2 *>(pwarp + fg * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][0], acc[n][1]);
-                *reinterpret_cast<float2 *>(pwarp + (fg + 8) * BM_NP + 8 * n + 2 * ft) = make_float2(acc[n][2], acc[n][3]);
-            }
-            bm_stamp(p, s, 3);
-            __syncthreads();
-            bm_stamp(p, s, 4);
-            if (owner) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < BM_NW; ++w) v += part[w * (BW_BT * BM_NP) + orow * BM_NP + oj];
-                dh += v;
-            }
-        }
 
-        // gate arithmetic; the bf16 planes the siblings wait for are published first, the fp32 arrays the weight GEMMs
-        // read follow after the release, off the chain
-        float rec[G], dxn = 0.f;
+                // gate arithmetic; the bf16 planes the siblings wait for are published first, the fp32 arrays the weight GEMMs
+                // read follow after the release, off the chain
+                float rec[G], dxn = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) rec[g] = 0.f;
-        if (oval) {
-            if constexpr (CELL == DL4SS_CELL_LSTM) {
-                const float ig = gv[0], fgt = gv[1], gg = gv[2], og = gv[3];
-                const float tc = tanhf(cv);
-                const float dc = fmaf(dh * og, 1.0f - tc * tc, carry);
-                rec[0] = dc * gg * ig * (1.0f - ig);
-                rec[1] = dc * pv * fgt * (1.0f - fgt);
-                rec[2] = dc * ig * (1.0f - gg * gg);
-                rec[3] = dh * tc * og * (1.0f - og);
-                carry = dc * fgt;
-            } else {
-                dh += carry;
-                const float rg = gv[0], zg = gv[1], ng = gv[2];
-                const float hn = cv;
-                const float dn = dh * (1.0f - zg);
-                dxn = dn * (1.0f - ng * ng);
-                rec[0] = dxn * hn * rg * (1.0f - rg);
-                rec[1] = dh * (pv - ng) * zg * (1.0f - zg);
-                rec[2] = dxn * rg;
-                carry = dh * zg;
-            }
-            __nv_bfloat16 *xh = p.xplanes + row * GHg + ou;
+                for (int g = 0; g < G; ++g) rec[g] = 0.f;
+                if (oval) {
+                    if constexpr (CELL == DL4SS_CELL_LSTM) {
+                        const float ig = gv[0], fgt = gv[1], gg = gv[2], og = gv[3];
+                        const float tc = tanhf(cv);
+                        const float dc = fmaf(dh * og, 1.0f - tc * tc, carry[ti]);
+                        rec[0] = dc * gg * ig * (1.0f - ig);
+                        rec[1] = dc * pv * fgt * (1.0f - fgt);
+                        rec[2] = dc * ig * (1.0f - gg * gg);
+                        rec[3] = dh * tc * og * (1.0f - og);
+                        carry[ti] = dc * fgt;
+                    } else {
+                        dh += carry[ti];
+                        const float rg = gv[0], zg = gv[1], ng = gv[2];
+                        const float hn = cv;
+                        const float dn = dh * (1.0f - zg);
+                        dxn = dn * (1.0f - ng * ng);
+                        rec[0] = dxn * hn * rg * (1.0f - rg);
+                        rec[1] = dh * (pv - ng) * zg * (1.0f - zg);
+                        rec[2] = dxn * rg;
+                        carry[ti] = dh * zg;
+                    }
+                    __nv_bfloat16 *xh = p.xplanes + row * GHg + ou;
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const __nv_bfloat16 hi = __float2bfloat16_rn(rec[g]);
-                xh[(size_t)g * H] = hi;
-                xh[plane_elems + (size_t)g * H] = __float2bfloat16_rn(rec[g] - __bfloat162float(hi));
-            }
-        }
-        if (s + 1 < T) {
-            bm_stamp(p, s, 5);
-            __syncthreads();
-            bm_stamp(p, s, 6);
-            if (tid == 0) {
-                // release = MEMBAR.GPU + RED, cumulative over the barrier above: a separate __threadfence() paid a second membar
-                asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
-            }
-            bm_stamp(p, s, 7);
-        }
-        if (oval) {
-            float *ox = p.dgx + row * GH + ou;
-            if constexpr (CELL == DL4SS_CELL_LSTM) {
+                    for (int g = 0; g < G; ++g) {
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(rec[g]);
+                        xh[(size_t)g * H] = hi;
+                        xh[plane_elems + (size_t)g * H] = __float2bfloat16_rn(rec[g] - __bfloat162float(hi));
+                    }
+                }
+                if (s == 0 && tid == 0) *early_flag = 0;
+                if (tr0) bm_stamp(p, s, 5);
+                // every thread is past the reduction (partial sums) and has published its cells
+                __syncthreads();
+                early = (*early_flag != 0);
+                if (tr0) bm_stamp(p, s, 6);
+                if (s + 1 < T && tid == 32 * (BM_NW - 2)) {
+                    // release = MEMBAR.GPU + RED, cumulative over the barrier above (a separate __threadfence() paid a second membar);
+                    // issued from warp 14, which owns no cells: the ~1.3 k cycles of the membar stall nobody's stores
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
+                }
+                if (tr0) bm_stamp(p, s, 7);
+                if (oval) {
+                    float *ox = p.dgx + row * GH + ou;
+                    if constexpr (CELL == DL4SS_CELL_LSTM) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) __stcs(ox + (size_t)g * H, rec[g]);
-            } else {
-                float *oh = p.dgh + row * GH + ou;
-                __stcs(ox, rec[0]); __stcs(ox + H, rec[1]); __stcs(ox + 2 * (size_t)H, dxn);
+                        for (int g = 0; g < G; ++g) __stcs(ox + (size_t)g * H, rec[g]);
+                    } else {
+                        float *oh = p.dgh + row * GH + ou;
+                        __stcs(ox, rec[0]); __stcs(ox + H, rec[1]); __stcs(ox + 2 * (size_t)H, dxn);
 #pragma unroll
-                for (int g = 0; g < G; ++g) __stcs(oh + (size_t)g * H, rec[g]);
+                        for (int g = 0; g < G; ++g) __stcs(oh + (size_t)g * H, rec[g]);
+                    }
+                }
             }
         }
     }
@@ -485,6 +555,7 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
 
 static long long *g_bwd_trace = nullptr;
 static int g_bwd_trace_steps = 0;
+static int g_bwd_tpc = [] { const char *e = getenv("DL4SS_BWD_TILES_PER_CTA"); return e ? atoi(e) : 0; }();   // A/B: force >= n tiles per CTA
 
 static int bwd_ghp(int GH) { return GH + ((8 - GH % 32 + 32) % 32); }   // row pitch == 8 (mod 32) floats: the 8 distinct
                                                                          // 16-byte chunks of a warp load tile the 32 banks
@@ -549,12 +620,17 @@ static int launch_rnn_bwd_tc(RnnBwdTcParams p, int rows_left, cudaStream_t st, i
                   per_sm * sm_count(), p.nslices);
         return DL4SS_EUNSUPPORTED;
     }
+    // as few tiles per CTA as the co-resident CTAs allow; up to BM_MAXT * max_tiles tiles per launch
     int tiles = cdiv(rows_left, BW_BT);
-    if (tiles > max_tiles) tiles = max_tiles;
+    if (tiles > max_tiles * BM_MAXT) tiles = max_tiles * BM_MAXT;
+    int tpc = cdiv(tiles, max_tiles);
+    if (g_bwd_tpc > tpc) tpc = g_bwd_tpc < BM_MAXT ? g_bwd_tpc : BM_MAXT;
     p.batch_tiles = tiles;
+    p.tpc = tpc;
+    p.ngroups = cdiv(tiles, tpc);
     *launched_rows = tiles * BW_BT;
     void *args[] = {(void *)&p};
-    DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * tiles * p.nslices), dim3(BM_THREADS), args, smem, st));
+    DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * p.ngroups * p.nslices), dim3(BM_THREADS), args, smem, st));
     count_launch();
     return DL4SS_OK;
 }
@@ -667,7 +743,7 @@ extern "C" int dl4ss_rnn_layer_bwd_tc(int cell, const float *dy, const float *wh
     RnnBwdTcParams p;
     p.dy = dy; p.whh = whh; p.gates = gates_save; p.cells = cell_save; p.y = y; p.dgx = dgx; p.dgh = dgh;
     p.xplanes = (__nv_bfloat16 *)xplanes;
-    p.B = B; p.T = T; p.H = H; p.GHg = p.pitch = p.nks = 0; p.batch_tiles = 0; p.nslices = 0;
+    p.B = B; p.T = T; p.H = H; p.GHg = p.pitch = p.nks = 0; p.batch_tiles = 0; p.nslices = 0; p.tpc = 1; p.ngroups = 0;
     p.trace = g_bwd_trace; p.trace_steps = g_bwd_trace_steps;
     unsigned *ctr = (unsigned *)workspace;
     int b0 = 0;
