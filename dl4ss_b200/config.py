@@ -65,3 +65,4 @@ TRAIN_PERSISTENT_BPTT = True
 # Not in the reference: run the dense contractions of the backward pass (dW = dY^T X, dX = dY W) on the tcgen05
 # bf16x3 projection kernel; False leaves them to the library GEMM (cuBLAS fp32).
 TRAIN_TC_GEMMS = True
+TRAIN_MN_GEMMS = True      # weight gradients from row-major planes (MN-major UMMA operands): no transposing split

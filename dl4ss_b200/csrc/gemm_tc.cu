@@ -249,10 +249,28 @@ __device__ __forceinline__ const EpiAttn &epi_of_split(const EpiAttn &e, int) { 
 // Work items are (tile, K split): nsplit > 1 cuts the k-blocks of every tile into nsplit ranges whose partial
 // accumulators meet in C through fp32 atomics -- for the backward contractions over B*T rows whose M x N output is a
 // handful of tiles (dW = dY^T X: 57 or 20 tiles on 148 SMs).
-template <typename Epi>
+// MN = true: both operands are MN-major ("transposed" GEMM, C[m][n] = sum_r A[r][m] * B[r][n]: the weight gradients
+// dW = dY^T X straight from the row-major bf16 planes of dY and X, no transposing split).  The contraction index r runs
+// over (utterance b, frame t): a k-block is 64 frames of one utterance, fetched as 64 x 64 boxes of a 4-D tensor map
+// (column, t, b, plane) -- frames past T arrive as zeros, and a per-operand frame shift (mn.shift_a / shift_b: the
+// recurrent weight gradients pair dgates[t] with h[t-1] or h[t+1]) is just a coordinate offset whose out-of-range rows
+// read zeros as well.  In shared memory an operand tile is [64-column atom][64 frames][128 B] (128B swizzle), which is the
+// canonical MN-major UMMA layout: leading-dimension offset = one atom (8 KB), stride offset = 8 frames (1 KB).
+struct MnMode {
+    int tchunks;      // 64-frame chunks per utterance
+    int shift_a, shift_b;
+    int col0_a, col0_b;   // first column of the operand inside its plane rows (a coordinate offset: no alignment demands)
+};
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <typename Epi, bool MN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   int M, int N, int kblocks, int m_tiles, int n_tiles, int nsplit, unsigned *sched, const Epi epi) {
+                   int M, int N, int kblocks, int m_tiles, int n_tiles, int nsplit, unsigned *sched, const Epi epi,
+                   const MnMode mn) {
     constexpr int NSTEP = EpiTraits<Epi>::NSTEP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -306,17 +324,31 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *st = tiles + (size_t)stage * TSTAGE_BYTES;
                     mbar_expect_tx(&full[stage], TSTAGE_BYTES);
-                    tma_load_3d(st, &tmap_a, &full[stage], kb * TBK, m0, 0);
-                    tma_load_3d(st + TA_BYTES, &tmap_a, &full[stage], kb * TBK, m0, 1);
-                    tma_load_3d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
-                    tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
+                    if constexpr (MN) {
+                        const int b = kb / mn.tchunks, t0 = (kb - b * mn.tchunks) * TBK;
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                            for (int j = 0; j < TBM / 64; ++j)
+                                tma_load_4d(st + pl * TA_BYTES + j * 8192, &tmap_a, &full[stage], mn.col0_a + m0 + 64 * j, t0 + mn.shift_a, b, pl);
+#pragma unroll
+                            for (int j = 0; j < TBN / 64; ++j)
+                                tma_load_4d(st + 2 * TA_BYTES + pl * TB_BYTES + j * 8192, &tmap_b, &full[stage], mn.col0_b + n0 + 64 * j,
+                                            t0 + mn.shift_b, b, pl);
+                        }
+                    } else {
+                        tma_load_3d(st, &tmap_a, &full[stage], kb * TBK, m0, 0);
+                        tma_load_3d(st + TA_BYTES, &tmap_a, &full[stage], kb * TBK, m0, 1);
+                        tma_load_3d(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
+                        tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
+                    }
                     if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-                        constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN);
+            constexpr uint32_t idesc = umma_idesc_bf16(TBM, TBN) | (MN ? ((1u << 15) | (1u << 16)) : 0u);   // bits 15 / 16: A / B MN-major
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int it = 0;; ++it) {
                 const int slot = it & (TC_RING - 1);
@@ -333,13 +365,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)stage * TSTAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TA_BYTES);
-                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * TA_BYTES), b_lo = umma_desc_sw128(sa + 2 * TA_BYTES + TB_BYTES);
+                    const uint64_t a_hi = MN ? umma_desc_mn_sw128(sa) : umma_desc_sw128(sa);
+                    const uint64_t a_lo = MN ? umma_desc_mn_sw128(sa + TA_BYTES) : umma_desc_sw128(sa + TA_BYTES);
+                    const uint64_t b_hi = MN ? umma_desc_mn_sw128(sa + 2 * TA_BYTES) : umma_desc_sw128(sa + 2 * TA_BYTES);
+                    const uint64_t b_lo = MN ? umma_desc_mn_sw128(sa + 2 * TA_BYTES + TB_BYTES) : umma_desc_sw128(sa + 2 * TA_BYTES + TB_BYTES);
+                    constexpr int KSTEP = MN ? (2048 >> 4) : 2;  // per 16-element k step: K-major +32 B, MN-major +16 frames x 128 B
 #pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) {        // +32 B per 16-element k step (>>4 = 2)
-                        umma_bf16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, ((kb - kb0) | k) != 0);
-                        umma_bf16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
-                        umma_bf16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    for (int k = 0; k < TBK / 16; ++k) {
+                        umma_bf16(d, a_hi + KSTEP * k, b_lo + KSTEP * k, idesc, ((kb - kb0) | k) != 0);
+                        umma_bf16(d, a_lo + KSTEP * k, b_hi + KSTEP * k, idesc, 1);
+                        umma_bf16(d, a_hi + KSTEP * k, b_hi + KSTEP * k, idesc, 1);
                     }
                     umma_commit(&empty[stage]);
                     if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
@@ -504,9 +539,17 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
     if (total < grid) grid = (int)total;
     auto kern = gemm_bf16x3_kernel<Epi>;
     DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, nsplit, sched_pair(st), epi);
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, Kp / TBK, m_tiles, n_tiles, nsplit, sched_pair(st), epi, MnMode{0, 0, 0, 0, 0});
     DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel");
     return DL4SS_OK;
+}
+
+// planes: bf16 [2][B][T][ld] (row-major frames); columns [0, cols) of them; box = 64 columns x 64 frames of one utterance, one plane
+static int make_mn_map(CUtensorMap *map, const void *planes, int cols, int ld, int B, int T) {
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2, (cuuint64_t)B * T * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TBK, 1, 1};
+    return make_bf16_map(map, planes, 4, dims, strides, box);
 }
 
 }  // namespace dl4ss
@@ -546,6 +589,42 @@ extern "C" int dl4ss_split_bf16_t(const float *x, long long ld, int R, int C, vo
     DL4SS_CHECK_ARG(grid.y < 65536, "split_bf16_t: too many rows");
     split_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, R, C, Rp, (__nv_bfloat16 *)planes);
     DL4SS_LAUNCH_CHECK("split_bf16_t_kernel");
+    return DL4SS_OK;
+}
+
+extern "C" int dl4ss_linear_tc_tn_splitk_fwd(const void *a_planes, int lda, int wa, int col0_a, int shift_a,
+                                             const void *b_planes, int ldb, int wb, int col0_b, int shift_b,
+                                             float *C, int ldc, int M, int N, int B, int T, void *stream) {
+    DL4SS_CHECK_ARG(a_planes && b_planes && C, "linear_tc_tn_splitk_fwd: null operand");
+    DL4SS_CHECK_ARG(M >= 1 && N >= 1 && B >= 0 && T >= 1 && ldc >= N && col0_a >= 0 && col0_b >= 0 && col0_a + M <= wa &&
+                    col0_b + N <= wb && wa <= lda && wb <= ldb,
+                    "linear_tc_tn_splitk_fwd: bad M/N/B/T/lda/wa/col0_a/ldb/wb/col0_b/ldc %d/%d/%d/%d/%d/%d/%d/%d/%d/%d/%d",
+                    M, N, B, T, lda, wa, col0_a, ldb, wb, col0_b, ldc);
+    DL4SS_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && (((uintptr_t)a_planes) & 15) == 0 && (((uintptr_t)b_planes) & 15) == 0,
+                    "linear_tc_tn_splitk_fwd: plane rows must be 16-byte aligned (pitch a multiple of 8 elements)");
+    DL4SS_CHECK_ARG(col0_a % 8 == 0 && col0_b % 8 == 0,
+                    "linear_tc_tn_splitk_fwd: col0_a / col0_b must be multiples of 8 (a TMA box starts on a 16-byte boundary)");
+    cudaStream_t st = (cudaStream_t)stream;
+    DL4SS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));   // the K splits meet in C through fp32 atomics
+    if (B == 0) return DL4SS_OK;
+    CUtensorMap ma, mb;
+    int rc = make_mn_map(&ma, a_planes, wa, lda, B, T);
+    if (rc) return rc;
+    rc = make_mn_map(&mb, b_planes, wb, ldb, B, T);
+    if (rc) return rc;
+    const int tchunks = cdiv(T, TBK);
+    const int kblocks = B * tchunks;
+    const int m_tiles = cdiv(M, TBM), n_tiles = cdiv(N, TBN);
+    const int ns = pick_ksplit((long long)m_tiles * n_tiles, kblocks, sm_count());
+    const long long total = (long long)m_tiles * n_tiles * ns;
+    int grid = sm_count();
+    if (g_max_ctas > 0 && g_max_ctas < grid) grid = g_max_ctas;
+    if (total < grid) grid = (int)total;
+    auto kern = gemm_bf16x3_kernel<EpiPlain<DL4SS_ACT_NONE, true>, true>;
+    DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, kblocks, m_tiles, n_tiles, ns, sched_pair(st),
+                                            EpiPlain<DL4SS_ACT_NONE, true>{C, nullptr, ldc}, MnMode{tchunks, shift_a, shift_b, col0_a, col0_b});
+    DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel<MN>");
     return DL4SS_OK;
 }
 

@@ -81,6 +81,22 @@ def matmul_tn(a2d, b2d):
     return linear_tc(split_bf16_t(a2d), split_bf16_t(b2d), None, a2d.shape[1], b2d.shape[1], R, split_k=True)
 
 
+def linear_tc_tn(a_planes, col0_a, M, shift_a, b_planes, col0_b, N, shift_b, B, T, wa=None, wb=None):
+    """sum over (b,t) of A[b,t+shift_a,col0_a+m] * B[b,t+shift_b,col0_b+n] -> [M,N] fp32 from ROW-major bf16 hi/lo planes
+    [2, B*T, ld] (MN-major UMMA operands: the weight gradients without a transposing split; out-of-range frames read zeros)."""
+    lib = _lib.load()
+    # a TMA box starts on a 16-byte boundary: windows that begin at an odd multiple of elements are widened to the left and
+    # the surplus rows / columns of the result dropped
+    pa, pb = col0_a % 8, col0_b % 8
+    out = torch.empty(M + pa, N + pb, device=a_planes.device, dtype=torch.float32)
+    lda, ldb = a_planes.shape[-1], b_planes.shape[-1]
+    rc = lib.dl4ss_linear_tc_tn_splitk_fwd(_lib.ptr(a_planes, torch.bfloat16), lda, lda if wa is None else wa, col0_a - pa, shift_a,
+                                           _lib.ptr(b_planes, torch.bfloat16), ldb, ldb if wb is None else wb, col0_b - pb, shift_b,
+                                           _lib.ptr(out), out.stride(0), M + pa, N + pb, B, T, _lib.stream())
+    _lib.check(rc, 'dl4ss_linear_tc_tn_splitk_fwd')
+    return out[pa:, pb:] if (pa or pb) else out
+
+
 def matmul_nn(a2d, w):
     """a2d @ w  ([M,K],[K,N] -> [M,N]) on tcgen05 (bf16x3): w is transposed once into the kernel's [N,K] operand form."""
     a2d = a2d if a2d.is_contiguous() else a2d.contiguous()
@@ -248,6 +264,7 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None):
     hmean = None
     Kpy = (2 * H + 63) // 64 * 64
     for li, lw in enumerate(layers):
+        a_pl = None
         if use_tensor_cores():
             x2d = inp.view(B * T, -1)
             a_pl = planes if planes is not None else split_bf16(x2d)
@@ -270,7 +287,8 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None):
         y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells, y_out, planes,
                             hmean if li == len(layers) - 1 else None)
         if save is not None:
-            save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells})
+            save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells,
+                         'x_planes': a_pl if use_tensor_cores() else None, 'y_planes': planes})
         inp = y
     if extras is not None:
         extras['planes'] = planes

@@ -422,21 +422,45 @@ class TrainStep(object):
                 # (columns [0,H): y[t-1] of the forward direction, [H,2H): y[t+1] of the reverse one; the rows without
                 # a predecessor stay zero) as the two diagonal blocks.
                 R = B * T
-                dg_t_planes = M.split_bf16_t(dgx2d)
-                dW_ih = M.linear_tc(dg_t_planes, M.split_bf16_t(x2d), None, 2 * G * H, x2d.shape[1], R, split_k=True)
-                ysh = st.get('ysh')
-                if ysh is None or ysh.shape != y.shape:
-                    ysh = torch.zeros_like(y)
-                    st['ysh'] = ysh
-                ysh[:, 1:, :H].copy_(y[:, :-1, :H])
-                ysh[:, :-1, H:].copy_(y[:, 1:, H:])
-                P = M.linear_tc(dg_t_planes, M.split_bf16_t(ysh.view(R, 2 * H)), None, 2 * G * H, 2 * H, R, split_k=True)
-                for d, suf in enumerate(('', '_reverse')):
-                    sl = slice(d * G * H, (d + 1) * G * H)
-                    _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
-                    _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
-                    _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)), P[sl, d * H:(d + 1) * H])
-                    _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), db_x[sl])
+                xp = st.get('xplanes') if persistent else None
+                GHg = (G * H + 7) // 8 * 8
+                if (config.TRAIN_MN_GEMMS and xp is not None and sv.get('x_planes') is not None and sv.get('y_planes') is not None
+                        and xp.numel() == 2 * R * 2 * GHg * 2):
+                    # MN-major operands: the BPTT kernel's bf16 planes of the gate gradients, the forward pass's planes of the
+                    # layer input and output are used as they lie (row-major): no transposing split, and the time shift of
+                    # the recurrent products is a TMA coordinate offset (frames outside the utterance read zeros)
+                    dg_pl = xp.view(torch.bfloat16).view(2, R, 2 * GHg)
+                    x_pl, y_pl = sv['x_planes'], sv['y_planes']
+                    nin = x2d.shape[1]
+                    dW_ih = M.linear_tc_tn(dg_pl, 0, 2 * G * H, 0, x_pl, 0, nin, 0, B, T, wa=2 * GHg, wb=nin) if GHg == G * H else None
+                    for d, suf in enumerate(('', '_reverse')):
+                        if dW_ih is None:
+                            dWd = M.linear_tc_tn(dg_pl, d * GHg, G * H, 0, x_pl, 0, nin, 0, B, T, wa=2 * GHg, wb=nin)
+                        else:
+                            dWd = dW_ih[d * G * H:(d + 1) * G * H]
+                        dWh = M.linear_tc_tn(dg_pl, d * GHg, G * H, 0, y_pl, d * H, H, -1 if d == 0 else 1, B, T,
+                                             wa=2 * GHg, wb=2 * H)
+                        sl = slice(d * G * H, (d + 1) * G * H)
+                        _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dWd)
+                        _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
+                        _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)), dWh)
+                        _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), db_x[sl])
+                else:
+                    dg_t_planes = M.split_bf16_t(dgx2d)
+                    dW_ih = M.linear_tc(dg_t_planes, M.split_bf16_t(x2d), None, 2 * G * H, x2d.shape[1], R, split_k=True)
+                    ysh = st.get('ysh')
+                    if ysh is None or ysh.shape != y.shape:
+                        ysh = torch.zeros_like(y)
+                        st['ysh'] = ysh
+                    ysh[:, 1:, :H].copy_(y[:, :-1, :H])
+                    ysh[:, :-1, H:].copy_(y[:, 1:, H:])
+                    P = M.linear_tc(dg_t_planes, M.split_bf16_t(ysh.view(R, 2 * H)), None, 2 * G * H, 2 * H, R, split_k=True)
+                    for d, suf in enumerate(('', '_reverse')):
+                        sl = slice(d * G * H, (d + 1) * G * H)
+                        _accum(getattr(rnn, 'weight_ih_l%d%s' % (l, suf)), dW_ih[sl])
+                        _accum(getattr(rnn, 'bias_ih_l%d%s' % (l, suf)), db_x[sl])
+                        _accum(getattr(rnn, 'weight_hh_l%d%s' % (l, suf)), P[sl, d * H:(d + 1) * H])
+                        _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), db_x[sl])
             else:
                 dW_ih = _mm_tn(dgx2d, x2d)                                       # [2*G*H, in]
                 dgr = dgh if gru else dgx                                        # recurrent-side gate grads

@@ -183,6 +183,16 @@ int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float 
  * launch when the tiles already fill the machine. */
 int dl4ss_linear_tc_splitk_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
                                int ldc, int M, int N, int K, void *stream);
+/* C[m][n] = sum over (b,t) of A[b][t + shift_a][col0_a + m] * B[b][t + shift_b][col0_b + n]   (m < M, n < N), fp32 results of
+ * bf16x3 products -- the weight gradients dW = dY^T X of the training step (TDAA_beta/main_run_sstune_EvalVer.py:673
+ * loss.backward()) straight from ROW-MAJOR bf16 hi/lo planes [2][B][T][ld] (wa / wb valid columns per row, pitch lda / ldb a
+ * multiple of 8 elements, 16-byte aligned; col0_a / col0_b multiples of 8): both UMMA operands are MN-major, so no transposed
+ * copy is made.  Frames outside
+ * [0,T) read as zeros, which is how the recurrent weight gradients pair dgates[t] with h[t-1] (shift_b = -1) or h[t+1] (+1)
+ * without a shifted copy.  The contraction is cut into splits that fill the SMs; C (pitch ldc) is zeroed by the callee. */
+int dl4ss_linear_tc_tn_splitk_fwd(const void *a_planes, int lda, int wa, int col0_a, int shift_a,
+                                  const void *b_planes, int ldb, int wb, int col0_b, int shift_b,
+                                  float *C, int ldc, int M, int N, int B, int T, void *stream);
 int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_planes, const float *bias,
                                const float *q, int B, int T, int F, int E, int K, int S, int mode,
                                float crm_k, float crm_c, float *mask_out, void *stream);

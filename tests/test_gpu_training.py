@@ -236,3 +236,44 @@ def test_pit_training_gradients(cuda):
             continue
         scale = max(gr.abs().max().item(), 1e-12)
         assert (g[k] - gr).abs().max().item() / scale < 2e-3, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,T,Ca,Cb,col0_a,M,col0_b,N,sa,sb', [(3, 70, 200, 129, 0, 200, 0, 129, 0, 0),
+                                                               (5, 313, 2400, 600, 1200, 1200, 300, 300, 0, 1),
+                                                               (4, 64, 320, 600, 0, 300, 0, 300, 0, -1),
+                                                               (2, 130, 136, 72, 8, 100, 3, 60, 1, 0)])
+def test_linear_tc_tn_matches_float64(cuda, B, T, Ca, Cb, col0_a, M, col0_b, N, sa, sb):
+    """MN-major split-K product (dl4ss_linear_tc_tn_splitk_fwd): sum over (b,t) of A[b,t+sa,col0_a+m] * B[b,t+sb,col0_b+n]
+    from row-major bf16 hi/lo planes, against float64 -- column windows, frame shifts (out-of-range frames are zeros),
+    T not a multiple of the 64-frame k-block, pitches that are not multiples of 64."""
+    import dl4ss_b200 as d
+    from dl4ss_b200 import modules as Mo
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    a = torch.randn(B, T, Ca, generator=g)
+    b = torch.randn(B, T, Cb, generator=g)
+
+    def planes(x):            # [2, B*T, ld] with ld = columns rounded up to 8 (not the 64 the K-major path wants)
+        C = x.shape[-1]
+        ld = (C + 7) // 8 * 8
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        out = torch.zeros(2, x.shape[0] * x.shape[1], ld, dtype=torch.bfloat16)
+        out[0, :, :C], out[1, :, :C] = hi.view(-1, C), lo.view(-1, C)
+        return out.to(cuda)
+
+    got = Mo.linear_tc_tn(planes(a), col0_a, M, sa, planes(b), col0_b, N, sb, B, T, wa=Ca, wb=Cb).cpu().double()
+
+    def shifted(x, s):
+        y = torch.zeros_like(x)
+        if s == 0:
+            y = x.clone()
+        elif s > 0:
+            y[:, :-s] = x[:, s:]
+        else:
+            y[:, -s:] = x[:, :s]
+        return y
+
+    want = torch.einsum('btm,btn->mn', shifted(a, sa)[:, :, col0_a:col0_a + M].double(), shifted(b, sb)[:, :, col0_b:col0_b + N].double())
+    err = (got - want).abs().max().item()
+    assert err < 3e-5 * want.abs().max().item(), err
