@@ -48,6 +48,7 @@ SIGNATURES = {
     'dl4ss_split_bf16_t': (c_i, [c_p, c_ll, c_i, c_i, c_p, c_p]),
     'dl4ss_linear_tc_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     'dl4ss_linear_tc_splitk_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    'dl4ss_linear_tc_lda_fwd': (c_i, [c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     'dl4ss_linear_tc_tn_splitk_fwd': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     'dl4ss_emb_attn_mask_tc_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_attn_dot_fwd': (c_i, [c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),

@@ -500,9 +500,11 @@ int make_f32_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t 
 }
 
 // planes: bf16 [2][R][Kp]; box = 64 (K) x rows x 1 plane, 128B swizzle, OOB rows zero-filled
-static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int Kp, int box_rows) {
-    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)R, 2};
-    cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
+static int make_plane_map(CUtensorMap *map, const void *planes, long long R, int Kp, int box_rows, int pitch = 0, int kvalid = 0) {
+    if (pitch <= 0) pitch = Kp;              // row pitch in elements; columns >= kvalid (default: the padded Kp) read as zeros
+    if (kvalid <= 0) kvalid = Kp;
+    cuuint64_t dims[3] = {(cuuint64_t)kvalid, (cuuint64_t)R, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)R * pitch * 2};
     cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
     return make_bf16_map(map, planes, 3, dims, strides, box);
 }
@@ -525,10 +527,10 @@ static int g_max_ctas = [] { const char *e = getenv("DL4SS_GEMM_MAX_CTAS"); retu
 
 template <typename Epi>
 static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, int K, int n_tiles, const Epi &epi,
-                     cudaStream_t st, int nsplit = 1) {
+                     cudaStream_t st, int nsplit = 1, int lda = 0) {
     const int Kp = (K + TBK - 1) / TBK * TBK;
     CUtensorMap ma, mb;
-    int rc = make_plane_map(&ma, a_planes, M, Kp, TBM);
+    int rc = make_plane_map(&ma, a_planes, M, Kp, TBM, lda, lda > 0 ? K : 0);
     if (rc) return rc;
     rc = make_plane_map(&mb, w_planes, N, Kp, TBN);        // rows past N (and past a tile's own rows) are ignored / zero
     if (rc) return rc;
@@ -639,6 +641,15 @@ extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, c
     if (act == DL4SS_ACT_SIGMOID)
         return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_SIGMOID>{C, bias, ldc}, (cudaStream_t)stream);
     return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream);
+}
+
+extern "C" int dl4ss_linear_tc_lda_fwd(const void *a_planes, int lda, const void *w_planes, const float *bias, float *C, int ldc,
+                                       int M, int N, int K, void *stream) {
+    DL4SS_CHECK_ARG(a_planes && w_planes && C, "linear_tc_lda_fwd: null operand");
+    DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N && lda >= K && lda % 8 == 0,
+                    "linear_tc_lda_fwd: bad M/N/K/ldc/lda %d/%d/%d/%d/%d (lda: a multiple of 8 elements)", M, N, K, ldc, lda);
+    if (M == 0) return DL4SS_OK;
+    return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream, 1, lda);
 }
 
 extern "C" int dl4ss_linear_tc_splitk_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,

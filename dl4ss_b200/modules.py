@@ -113,6 +113,15 @@ def weight_planes(w):
     return ent[2]
 
 
+def weight_t_planes(w):
+    """bf16 planes of w^T ([K,N] weight used as the [N,K] operand of `a @ w`), cached like `weight_planes`."""
+    ent = getattr(w, '_dl4ss_planes_t', None)
+    if ent is None or ent[0] != w._version or ent[1] != w.data_ptr():
+        ent = (w._version, w.data_ptr(), split_bf16(w.detach().t().contiguous()))
+        w._dl4ss_planes_t = ent
+    return ent[2]
+
+
 def linear_tc(a_planes, w_planes, bias, M, N, K, out=None, act='none', split_k=False):
     """act(a[M,K] @ w[N,K]^T + bias) from pre-split planes on tcgen05 (bf16x3, fp32 accumulate).
     split_k: let the kernel cut K into splits that fill the SMs when the output is only a few tiles (act 'none')."""

@@ -477,7 +477,20 @@ class TrainStep(object):
                     _accum(getattr(rnn, 'bias_hh_l%d%s' % (l, suf)), dgr[:, :, d, :].sum((0, 1)))
             self._segment_done(rnn.num_layers - l)      # this layer's gradients: reduced under the layers below
             if l > 0:
-                dy = _mm_nn(dgx2d, lw['wih']).view(B, T, -1).contiguous()
+                xp = st.get('xplanes') if (persistent and not gru) else None
+                GHg = (G * H + 7) // 8 * 8
+                if (M.use_tensor_cores() and config.TRAIN_TC_GEMMS and config.TRAIN_MN_GEMMS and xp is not None and GHg == G * H
+                        and xp.numel() == 2 * B * T * 2 * GHg * 2):
+                    # dX = dgates W_ih from the BPTT kernel's planes as they lie (row pitch 2*G*H): no split of dgx
+                    nin = lw['wih'].shape[1]
+                    out = torch.empty(B * T, nin, device=dev, dtype=torch.float32)
+                    rc = _lib.load().dl4ss_linear_tc_lda_fwd(ctypes.c_void_p(xp.data_ptr()), 2 * GHg,
+                                                             _lib.ptr(M.weight_t_planes(lw['wih']), torch.bfloat16), None,
+                                                             _lib.ptr(out), nin, B * T, nin, 2 * G * H, _lib.stream())
+                    _lib.check(rc, 'dl4ss_linear_tc_lda_fwd')
+                    dy = out.view(B, T, -1)
+                else:
+                    dy = _mm_nn(dgx2d, lw['wih']).view(B, T, -1).contiguous()
 
     # ------------------------------------------------------------------------------ full step
     def step(self, optimizer, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, group=None, overlap=True,

@@ -176,6 +176,11 @@ int dl4ss_split_bf16(const float *x, int ld, long long R, int K, void *planes, v
 int dl4ss_split_bf16_t(const float *x, long long ld, int R, int C, void *planes, void *stream);
 int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, const float *bias, float *C,
                         int ldc, int M, int N, int K, int act, void *stream);
+/* dl4ss_linear_tc_fwd (act none) whose A planes have row pitch lda >= K elements (a multiple of 8) instead of K rounded up to
+ * 64: [2][M][lda]; columns [K, lda) are never read (the k tail of the last block reads as zeros).  Lets a producer's planes
+ * (e.g. the BPTT kernel's gate-gradient planes, pitch 2*G*H) feed the projection as they lie. */
+int dl4ss_linear_tc_lda_fwd(const void *a_planes, int lda, const void *w_planes, const float *bias, float *C, int ldc,
+                            int M, int N, int K, void *stream);
 /* Same contraction without an activation, for outputs of only a few 128x256 tiles and a long K (the backward
  * contractions over B*T rows, dW = dY^T X): the k-blocks of every tile are cut into as many splits as fill the
  * SMs and the partial tiles meet in C through fp32 atomic adds (C is zeroed by the callee; the summation order of
