@@ -60,6 +60,7 @@ SIGNATURES = {
     'dl4ss_rowdot_sigmoid_fwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     'dl4ss_mask_loss_bwd': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p]),
     'dl4ss_attn_dot_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    'dl4ss_attn_dot_bwd_planes': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_i, c_p, c_p]),
     'dl4ss_rnn_bwd_step': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     'dl4ss_rnn_bwd_supported': (c_i, [c_i, c_i]),
     'dl4ss_rnn_bwd_set_trace': (None, [c_p, c_i]),

@@ -8,6 +8,7 @@
 // The dense contractions of the backward pass (dW, dx, dh, and the per-step dh_rec = dgates * W_hh) are plain
 // GEMMs issued by the host code through cuBLAS this round; everything fused or element-wise is here.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace dl4ss {
 
@@ -45,11 +46,15 @@ mask_loss_bwd_kernel(const float *__restrict__ mask, const float *__restrict__ m
 // ----------------------------------------------------------------------------------------- attention backward
 constexpr int AB_ROWS = 128;
 
-template <int MODE>
+// PLANES: dz leaves as bf16 hi/lo planes [2][B*T][ldp] (row (b,t), column f*E+e) -- the operand form of the two GEMMs that
+// consume it (dW_lin = dz^T h with MN-major operands, dh = dz W_lin) -- instead of fp32: the same 4 bytes per value, and no
+// split passes over the 2 GB tensor afterwards.
+template <int MODE, bool PLANES>
 __global__ void __launch_bounds__(AB_ROWS)
 attn_dot_bwd_kernel(const float *__restrict__ emb, const float *__restrict__ q, const float *__restrict__ mask,
                     const float *__restrict__ dmask, int S, int TF, int E, float crm_k, float crm_c,
-                    float *__restrict__ dz, float *__restrict__ dq) {
+                    float *__restrict__ dz, float *__restrict__ dq, __nv_bfloat16 *__restrict__ planes, int F, int ldp,
+                    size_t plane_elems, size_t row_base) {
     extern __shared__ __align__(16) float sm[];
     const int NQ = (MODE == DL4SS_ATT_DOT_CRM) ? 2 : 1;        // energies per speaker
     const int EQ = NQ * E;
@@ -113,8 +118,21 @@ attn_dot_bwd_kernel(const float *__restrict__ emb, const float *__restrict__ q, 
         }
     }
     __syncthreads();
-    float *dst = dz + ((size_t)b * TF + r0) * E;
-    for (int i = tid; i < nrows * E; i += AB_ROWS) dst[i] = tile[(i / E) * EP + (i % E)];
+    if constexpr (PLANES) {
+        const int T = TF / F;
+        for (int i = tid; i < nrows * E; i += AB_ROWS) {
+            const int r = i / E, e = i - r * E;
+            const int tf = r0 + r, t = tf / F, f = tf - t * F;
+            const float v = tile[r * EP + e];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const size_t o = (row_base + (size_t)b * T + t) * ldp + (size_t)f * E + e;
+            planes[o] = hi;
+            planes[plane_elems + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+    } else {
+        float *dst = dz + ((size_t)b * TF + r0) * E;
+        for (int i = tid; i < nrows * E; i += AB_ROWS) dst[i] = tile[(i / E) * EP + (i % E)];
+    }
 }
 
 // ----------------------------------------------------------------------------------------- BPTT step
@@ -196,10 +214,10 @@ extern "C" int dl4ss_mask_loss_bwd(const float *mask, int mask_kind, const float
     return DL4SS_OK;
 }
 
-extern "C" int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float *mask, const float *dmask, int B,
-                                  int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
-                                  void *stream) {
-    DL4SS_CHECK_ARG(emb && q && mask && dmask && dz && dq, "attn_dot_bwd: null operand");
+static int attn_dot_bwd_impl(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                             int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
+                             __nv_bfloat16 *planes, int F, int ldp, void *stream) {
+    DL4SS_CHECK_ARG(emb && q && mask && dmask && (dz || planes) && dq, "attn_dot_bwd: null operand");
     DL4SS_CHECK_ARG(mode == DL4SS_ATT_DOT || mode == DL4SS_ATT_DOT_CRM, "attn_dot_bwd: bad mode %d", mode);
     const int NQ = (mode == DL4SS_ATT_DOT_CRM) ? 2 : 1;
     DL4SS_CHECK_ARG(B >= 0 && S >= 1 && S * NQ <= 8 && TF >= 1 && E >= 1, "attn_dot_bwd: bad shape (S*%d <= 8)", NQ);
@@ -215,17 +233,37 @@ extern "C" int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float 
         const int nb = (B - b0 < 65535) ? B - b0 : 65535;
         dim3 grid(cdiv(TF, AB_ROWS), nb);
         const size_t mo = (size_t)b0 * S * TF * NQ;
-#define LAUNCH_AB(MODE)                                                                                          \
+        const size_t plane_elems = planes ? (size_t)B * (TF / F) * ldp : 0;
+        const size_t row_base = planes ? (size_t)b0 * (TF / F) : 0;
+#define LAUNCH_AB(MODE, PL)                                                                                      \
         do {                                                                                                     \
-            DL4SS_CUDA(cudaFuncSetAttribute(attn_dot_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attn_dot_bwd_kernel<MODE><<<grid, AB_ROWS, smem, st>>>(emb + (size_t)b0 * TF * E, q + (size_t)b0 * S * NQ * E, \
-                mask + mo, dmask + mo, S, TF, E, crm_k, crm_c, dz + (size_t)b0 * TF * E, dq + (size_t)b0 * S * NQ * E); \
+            DL4SS_CUDA(cudaFuncSetAttribute(attn_dot_bwd_kernel<MODE, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attn_dot_bwd_kernel<MODE, PL><<<grid, AB_ROWS, smem, st>>>(emb + (size_t)b0 * TF * E, q + (size_t)b0 * S * NQ * E, \
+                mask + mo, dmask + mo, S, TF, E, crm_k, crm_c, dz ? dz + (size_t)b0 * TF * E : nullptr,            \
+                dq + (size_t)b0 * S * NQ * E, planes, F, ldp, plane_elems, row_base);                             \
         } while (0)
-        if (mode == DL4SS_ATT_DOT) LAUNCH_AB(DL4SS_ATT_DOT); else LAUNCH_AB(DL4SS_ATT_DOT_CRM);
+        if (planes) { if (mode == DL4SS_ATT_DOT) LAUNCH_AB(DL4SS_ATT_DOT, true); else LAUNCH_AB(DL4SS_ATT_DOT_CRM, true); }
+        else { if (mode == DL4SS_ATT_DOT) LAUNCH_AB(DL4SS_ATT_DOT, false); else LAUNCH_AB(DL4SS_ATT_DOT_CRM, false); }
 #undef LAUNCH_AB
         DL4SS_LAUNCH_CHECK("attn_dot_bwd_kernel");
     }
     return DL4SS_OK;
+}
+
+extern "C" int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                                  int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
+                                  void *stream) {
+    DL4SS_CHECK_ARG(dz, "attn_dot_bwd: null operand");
+    return attn_dot_bwd_impl(emb, q, mask, dmask, B, S, TF, E, mode, crm_k, crm_c, dz, dq, nullptr, 1, 0, stream);
+}
+
+extern "C" int dl4ss_attn_dot_bwd_planes(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                                         int S, int T, int F, int E, int mode, float crm_k, float crm_c, void *dz_planes,
+                                         int ldp, float *dq, void *stream) {
+    DL4SS_CHECK_ARG(dz_planes && T >= 1 && F >= 1 && ldp >= F * E && ldp % 8 == 0 && (((uintptr_t)dz_planes) & 15) == 0,
+                    "attn_dot_bwd_planes: dz_planes null / misaligned or bad T/F/ldp %d/%d/%d (ldp >= F*E, a multiple of 8)", T, F, ldp);
+    return attn_dot_bwd_impl(emb, q, mask, dmask, B, S, T * F, E, mode, crm_k, crm_c, nullptr, dq,
+                             (__nv_bfloat16 *)dz_planes, F, ldp, stream);
 }
 
 extern "C" int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, const float *gates_save,

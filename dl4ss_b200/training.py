@@ -168,6 +168,7 @@ class TrainStep(object):
         self.complex_mask = bool(config.is_ComlexMask)
         self._bptt = {}           # (layer, B, T) -> static buffers + captured BPTT graph
         self._bucket = None       # GradBucket: created by step() on first use
+        self._dz_planes = None    # bf16 hi/lo planes of d(loss)/d(pre-tanh embedding), reused across steps
         self._reduce = None       # (bucket, group) while a step() wants its segments reduced as they complete
         self.reduced_bytes = 0
 
@@ -212,7 +213,9 @@ class TrainStep(object):
         bufs = None
         if config.TRAIN_CUDA_GRAPHS:       # static per-layer buffers so the BPTT chain can be replayed from a graph
             bufs = [self._bptt_state(l, B, T, mix_feas.device) for l in range(self.mix.layer.num_layers)]
-        hidden = M.rnn_forward(self.mix._packed, mix_feas, save=saved, buffers=bufs)   # K2 + K3, gates saved
+        ex = {}
+        hidden = M.rnn_forward(self.mix._packed, mix_feas, save=saved, buffers=bufs, extras=ex)   # K2 + K3, gates saved
+        h_planes = ex.get('planes')            # the top layer's output as bf16 hi/lo planes [2, B*T, Kpy] (fused by K3)
         idx = self.emb.index_tensor(spk_idx)
         table = self.emb.layer.weight
         e = table.detach()[idx]                                                   # [B,S,EQ] gather (glue)
@@ -228,8 +231,12 @@ class TrainStep(object):
         K = hidden.shape[2]
         h2d = hidden.view(B * T, K)
         if M.use_tensor_cores():
-            emb = M.linear_tc(M.split_bf16(h2d), M.weight_planes(lin.weight), lin.bias.detach(), B * T, F * E, K,
-                              act='tanh')
+            if h_planes is not None and h_planes.shape[-1] > K:
+                # a column of ones next to the K outputs: the weight-gradient GEMM over these planes then yields the bias
+                # gradient as its last column (the forward product meets zero padding of the weight planes there)
+                h_planes[0, :, K].fill_(1.0)
+            emb = M.linear_tc(h_planes if h_planes is not None else M.split_bf16(h2d), M.weight_planes(lin.weight),
+                              lin.bias.detach(), B * T, F * E, K, act='tanh')
         else:
             emb = M.linear_fwd(h2d, lin.weight.detach(), lin.bias.detach(), 'tanh')
         cplx = self.complex_mask
@@ -239,7 +246,7 @@ class TrainStep(object):
                                     float(config.cRM_k), float(config.cRM_C), _lib.ptr(masks), _lib.stream())
         _lib.check(rc, 'dl4ss_attn_dot_fwd')
         return {'B': B, 'T': T, 'F': F, 'E': E, 'S': S, 'EQ': EQ, 'saved': saved, 'hidden': hidden, 'idx': idx,
-                'e': e, 'hmean': hmean, 'q': q, 'emb': emb, 'masks': masks, 'x0': mix_feas}
+                'e': e, 'hmean': hmean, 'q': q, 'emb': emb, 'masks': masks, 'x0': mix_feas, 'h_planes': h_planes}
 
     # ------------------------------------------------------------------------------ loss + backward
     def loss_and_grads(self, mix_feas, spk_idx, target, mix_mag=None, global_batch=None, grad_scale=1.0, pit=False):
@@ -288,16 +295,40 @@ class TrainStep(object):
         mode = _lib.ATT_DOT_CRM if cplx else _lib.ATT_DOT
         emb, q, masks, hidden = ctx['emb'], ctx['q'], ctx['masks'], ctx['hidden']
         dq = torch.empty_like(q)
-        # attention + tanh backward: emb is overwritten by dz
-        rc = lib.dl4ss_attn_dot_bwd(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(masks), _lib.ptr(dmask), B, S, T * F, E, mode,
-                                    float(config.cRM_k), float(config.cRM_C), _lib.ptr(emb), _lib.ptr(dq), _lib.stream())
-        _lib.check(rc, 'dl4ss_attn_dot_bwd')
-        dz = emb.view(B * T, F * E)
         lin = self.mix.Linear
         h2d = hidden.view(B * T, -1)
-        _accum(lin.weight, _mm_tn(dz, h2d))
-        _accum(lin.bias, dz.sum(0))
-        dh = _mm_nn(dz, lin.weight.detach()).view(B, T, -1)
+        K = h2d.shape[1]
+        h_planes = ctx.get('h_planes')
+        if (M.use_tensor_cores() and config.TRAIN_TC_GEMMS and config.TRAIN_MN_GEMMS and h_planes is not None
+                and h_planes.shape[-1] > K):
+            # attention + tanh backward with dz emitted as bf16 planes: dW_lin (+ the bias gradient, through the ones column of
+            # the h planes) from MN-major operands and dh from the same planes -- no fp32 dz, no split passes over it
+            ldp = (F * E + 7) // 8 * 8
+            dzp = self._dz_planes
+            if dzp is None or dzp.shape != (2, B * T, ldp) or dzp.device != emb.device:
+                dzp = torch.zeros(2, B * T, ldp, device=emb.device, dtype=torch.bfloat16)      # pad columns stay zero
+                self._dz_planes = dzp
+            rc = lib.dl4ss_attn_dot_bwd_planes(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(masks), _lib.ptr(dmask), B, S, T, F, E, mode,
+                                               float(config.cRM_k), float(config.cRM_C), _lib.ptr(dzp, torch.bfloat16), ldp,
+                                               _lib.ptr(dq), _lib.stream())
+            _lib.check(rc, 'dl4ss_attn_dot_bwd_planes')
+            wext = M.linear_tc_tn(dzp, 0, F * E, 0, h_planes, 0, K + 1, 0, B, T, wa=F * E, wb=K + 1)   # [F*E, K+1]
+            _accum(lin.weight, wext[:, :K])
+            _accum(lin.bias, wext[:, K])
+            dh = torch.empty(B * T, K, device=emb.device, dtype=torch.float32)
+            rc = lib.dl4ss_linear_tc_lda_fwd(_lib.ptr(dzp, torch.bfloat16), ldp, _lib.ptr(M.weight_t_planes(lin.weight), torch.bfloat16),
+                                             None, _lib.ptr(dh), K, B * T, K, F * E, _lib.stream())
+            _lib.check(rc, 'dl4ss_linear_tc_lda_fwd')
+            dh = dh.view(B, T, -1)
+        else:
+            # attention + tanh backward: emb is overwritten by dz
+            rc = lib.dl4ss_attn_dot_bwd(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(masks), _lib.ptr(dmask), B, S, T * F, E, mode,
+                                        float(config.cRM_k), float(config.cRM_C), _lib.ptr(emb), _lib.ptr(dq), _lib.stream())
+            _lib.check(rc, 'dl4ss_attn_dot_bwd')
+            dz = emb.view(B * T, F * E)
+            _accum(lin.weight, _mm_tn(dz, h2d))
+            _accum(lin.bias, dz.sum(0))
+            dh = _mm_nn(dz, lin.weight.detach()).view(B, T, -1)
         # speaker query backward (tiny: glue in torch)
         table = self.emb.layer.weight
         if self.adj is not None:

@@ -287,6 +287,12 @@ int dl4ss_mask_loss_bwd(const float *mask, int mask_kind, const float *mix, cons
 int dl4ss_attn_dot_bwd(const float *emb, const float *q, const float *mask, const float *dmask, int B,
                        int S, int TF, int E, int mode, float crm_k, float crm_c, float *dz, float *dq,
                        void *stream);
+/* the same with dz emitted as bf16 hi/lo planes [2][B*T][ldp] (row (b,t), column f*E + e; ldp >= F*E, a multiple of 8; pad
+ * columns are left untouched: zero them once) instead of fp32 -- the operand form of the GEMMs that consume dz
+ * (dl4ss_linear_tc_tn_splitk_fwd for dW_lin, dl4ss_linear_tc_lda_fwd for dh); emb is only read */
+int dl4ss_attn_dot_bwd_planes(const float *emb, const float *q, const float *mask, const float *dmask, int B,
+                              int S, int T, int F, int E, int mode, float crm_k, float crm_c, void *dz_planes,
+                              int ldp, float *dq, void *stream);
 int dl4ss_rnn_bwd_step(int cell, int s, const float *dy, const float *dh_rec, const float *gates_save,
                        const float *cell_save, const float *y, float *carry, float *dgx, float *dgh,
                        float *dg_cur, int B, int T, int H, void *stream);
