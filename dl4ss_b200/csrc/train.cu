@@ -120,14 +120,28 @@ attn_dot_bwd_kernel(const float *__restrict__ emb, const float *__restrict__ q, 
     __syncthreads();
     if constexpr (PLANES) {
         const int T = TF / F;
-        for (int i = tid; i < nrows * E; i += AB_ROWS) {
-            const int r = i / E, e = i - r * E;
-            const int tf = r0 + r, t = tf / F, f = tf - t * F;
-            const float v = tile[r * EP + e];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const size_t o = (row_base + (size_t)b * T + t) * ldp + (size_t)f * E + e;
-            planes[o] = hi;
-            planes[plane_elems + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        if ((E & 1) == 0) {          // two values per thread: 4-byte stores (ldp and f*E + e are even)
+            const int E2 = E >> 1;
+            for (int i = tid; i < nrows * E2; i += AB_ROWS) {
+                const int r = i / E2, e = 2 * (i - r * E2);
+                const int tf = r0 + r, t = tf / F, f = tf - t * F;
+                const float v0 = tile[r * EP + e], v1 = tile[r * EP + e + 1];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                const size_t o = (row_base + (size_t)b * T + t) * ldp + (size_t)f * E + e;
+                *reinterpret_cast<__nv_bfloat162 *>(planes + o) = __halves2bfloat162(h0, h1);
+                *reinterpret_cast<__nv_bfloat162 *>(planes + plane_elems + o) =
+                    __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+            }
+        } else {
+            for (int i = tid; i < nrows * E; i += AB_ROWS) {
+                const int r = i / E, e = i - r * E;
+                const int tf = r0 + r, t = tf / F, f = tf - t * F;
+                const float v = tile[r * EP + e];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const size_t o = (row_base + (size_t)b * T + t) * ldp + (size_t)f * E + e;
+                planes[o] = hi;
+                planes[plane_elems + o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+            }
         }
     } else {
         float *dst = dz + ((size_t)b * TF + r0) * E;
