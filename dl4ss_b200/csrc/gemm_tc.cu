@@ -33,6 +33,12 @@ constexpr int TC_STORE_WARPS = 8;                             // warps of the pl
 constexpr size_t TC_SMEM = (size_t)TSTAGES * TSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                            (size_t)TC_STORE_WARPS * 32 * TC_STAGE_PITCH * sizeof(float);
 
+__device__ __forceinline__ bool elect_one_lane() {       // one lane of the converged warp (elect.sync: ptxas then emits straight-line uniform-datapath code)
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------ split
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ x, int ld, long long R, int K, int Kp, __nv_bfloat16 *__restrict__ planes) {
@@ -425,6 +431,159 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ 2-CTA kernel
+// The plain projection is bound by the SM-to-L2 port, not by the tensor pipe: a k-block moves 96 KB of operands per SM
+// (A hi/lo 32 KB + W hi/lo 64 KB) next to the 131 KB fp32 output tile.  Here two CTAs of a cluster (the two SMs of a TPC)
+// work on ONE 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA loads its own 128 rows of A and only HALF of the W tile
+// (128 of the 256 columns), the pair's tensor cores read both halves (the peer's through distributed shared memory): 64 KB of
+// operands per SM and k-block, three stages instead of two.  Roles per CTA as in the 1-CTA kernel; differences:
+//   * TMA loads carry .cta_group::2 and signal the LEADER's (cluster rank 0) `full` barrier: its address with the peer bit
+//     cleared; the leader expects the bytes of both CTAs;
+//   * only the leader's MMA lane issues UMMAs (M = 256: 128 accumulator rows in each CTA's tensor memory); its commits are
+//     multicast to the `empty` / `tfull` barriers of both CTAs;
+//   * the epilogue warps of both CTAs arrive on the leader's `tempty` (remote mbarrier arrive);
+//   * tensor memory is allocated with .cta_group::2 by the same warp of both CTAs; cluster barriers bracket the kernel so that
+//     no CTA exits while its peer may still touch its shared memory.
+constexpr int T2_STAGES = 3;
+constexpr int T2_BHALF = TBN / 2;                                 // W rows (output columns) each CTA holds
+constexpr int T2_B_BYTES = T2_BHALF * TBK * 2;                    // 16 KB
+constexpr int T2_STAGE_BYTES = 2 * TA_BYTES + 2 * T2_B_BYTES;     // 64 KB per CTA
+constexpr size_t T2_SMEM = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                           (size_t)TC_STORE_WARPS * 32 * TC_STAGE_PITCH * sizeof(float);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                       // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ void tma_load_3d_2sm(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {          // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {       // the same barrier in the pair's rank-0 CTA
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <typename Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    int M, int N, int kblocks, int m_tiles2, int n_tiles, const Epi epi) {
+    constexpr int NSTEP = EpiTraits<Epi>::NSTEP;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)T2_STAGES * T2_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + T2_STAGES, *tfull = bars + 2 * T2_STAGES, *tempty = bars + 2 * T2_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * T2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int total_work = m_tiles2 * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * 4 * EpiTraits<Epi>::PARTS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                       // the peer's barriers are initialised before anything is signalled on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one_lane()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = pair; w < total_work; w += npairs) {
+                const int m0 = (w / n_tiles) * (2 * TBM) + (int)rank * TBM, n0 = (w % n_tiles) * NSTEP + (int)rank * T2_BHALF;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char *st = tiles + (size_t)stage * T2_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * T2_STAGE_BYTES);       // both CTAs' bytes land on this barrier
+                    tma_load_3d_2sm(st, &tmap_a, &full[stage], kb * TBK, m0, 0);
+                    tma_load_3d_2sm(st + TA_BYTES, &tmap_a, &full[stage], kb * TBK, m0, 1);
+                    tma_load_3d_2sm(st + 2 * TA_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 0);
+                    tma_load_3d_2sm(st + 2 * TA_BYTES + T2_B_BYTES, &tmap_b, &full[stage], kb * TBK, n0, 1);
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one_lane()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * TBM, TBN);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int w = pair; w < total_work; w += npairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * TBN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * T2_STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TA_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(sa + 2 * TA_BYTES), b_lo = umma_desc_sw128(sa + 2 * TA_BYTES + T2_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; ++k) {
+                        umma_bf16_2sm(d, a_hi + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16_2sm(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+                        umma_bf16_2sm(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    }
+                    umma_commit_2sm(&empty[stage]);
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (((warp - 2) >> 2) < EpiTraits<Epi>::PARTS) {
+        const int quarter = warp & 3;
+        const int part = (warp - 2) >> 2;
+        float *stage = reinterpret_cast<float *>(tiles + (size_t)T2_STAGES * T2_STAGE_BYTES + 256) +
+                       (size_t)((part * 4 + quarter) % TC_STORE_WARPS) * 32 * TC_STAGE_PITCH;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = pair; w < total_work; w += npairs) {
+            const int m0 = (w / n_tiles) * (2 * TBM) + (int)rank * TBM, n0 = (w % n_tiles) * NSTEP;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TBN;
+            epilogue_tile(epi, taddr, m0 + quarter * 32, n0, M, N, part, lane, stage);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                       // the peer is done with this CTA's shared memory, barriers and tensor memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 // Counter pairs {next item, CTAs finished} of the dynamically scheduled launches, zeroed once; a launch takes one pair,
 // its last CTA re-zeroes it.  Eager launches cycle through a ring (far longer than any launch queue); launches recorded
@@ -546,6 +705,44 @@ static int launch_tc(const void *a_planes, const void *w_planes, int M, int N, i
     return DL4SS_OK;
 }
 
+static int g_two_cta = [] { const char *e = getenv("DL4SS_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+
+// the 2-CTA (cta_group::2) form of launch_tc for the plain epilogue: used when a launch owns the GPU (no CTA cap: with two
+// batches in flight the recurrent launch of the other batch leaves single SMs free, not TPC pairs) and the output is at
+// least one 256-row tile pair per SM pair
+template <typename Epi>
+static int launch_tc2(const void *a_planes, const void *w_planes, int M, int N, int K, const Epi &epi, cudaStream_t st, int lda = 0) {
+    const int Kp = (K + TBK - 1) / TBK * TBK;
+    CUtensorMap ma, mb;
+    int rc = make_plane_map(&ma, a_planes, M, Kp, TBM, lda, lda > 0 ? K : 0);
+    if (rc) return rc;
+    rc = make_plane_map(&mb, w_planes, N, Kp, T2_BHALF);
+    if (rc) return rc;
+    const int m_tiles2 = cdiv(M, 2 * TBM), n_tiles = cdiv(N, TBN);
+    const long long total = (long long)m_tiles2 * n_tiles;
+    int pairs = sm_count() / 2;
+    if (g_max_ctas > 0 && g_max_ctas / 2 < pairs) pairs = g_max_ctas / 2;
+    if (total < pairs) pairs = (int)total;
+    auto kern = gemm2_bf16x3_kernel<Epi>;
+    DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = T2_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DL4SS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, Kp / TBK, m_tiles2, n_tiles, epi));
+    count_launch();
+    return DL4SS_OK;
+}
+static bool use_two_cta(int M, int N) {
+    return g_two_cta != 0 && (g_max_ctas == 0 || g_two_cta == 2) && (long long)cdiv(M, 2 * TBM) * cdiv(N, TBN) >= sm_count() / 2;
+}
+
 // planes: bf16 [2][B][T][ld] (row-major frames); columns [0, cols) of them; box = 64 columns x 64 frames of one utterance, one plane
 static int make_mn_map(CUtensorMap *map, const void *planes, int cols, int ld, int B, int T) {
     cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B, 2};
@@ -636,10 +833,13 @@ extern "C" int dl4ss_linear_tc_fwd(const void *a_planes, const void *w_planes, c
     DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N, "linear_tc_fwd: bad M/N/K/ldc %d/%d/%d/%d", M, N, K, ldc);
     if (M == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG(act >= DL4SS_ACT_NONE && act <= DL4SS_ACT_SIGMOID, "linear_tc_fwd: bad act %d", act);
+    if (act == DL4SS_ACT_TANH && use_two_cta(M, N))
+        return launch_tc2(a_planes, w_planes, M, N, K, EpiPlain<DL4SS_ACT_TANH>{C, bias, ldc}, (cudaStream_t)stream);
     if (act == DL4SS_ACT_TANH)
         return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_TANH>{C, bias, ldc}, (cudaStream_t)stream);
     if (act == DL4SS_ACT_SIGMOID)
         return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_SIGMOID>{C, bias, ldc}, (cudaStream_t)stream);
+    if (use_two_cta(M, N)) return launch_tc2(a_planes, w_planes, M, N, K, EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream);
     return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream);
 }
 
@@ -649,6 +849,7 @@ extern "C" int dl4ss_linear_tc_lda_fwd(const void *a_planes, int lda, const void
     DL4SS_CHECK_ARG(M >= 0 && N >= 1 && K >= 1 && ldc >= N && lda >= K && lda % 8 == 0,
                     "linear_tc_lda_fwd: bad M/N/K/ldc/lda %d/%d/%d/%d/%d (lda: a multiple of 8 elements)", M, N, K, ldc, lda);
     if (M == 0) return DL4SS_OK;
+    if (use_two_cta(M, N)) return launch_tc2(a_planes, w_planes, M, N, K, EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream, lda);
     return launch_tc(a_planes, w_planes, M, N, K, cdiv(N, TBN), EpiPlain<DL4SS_ACT_NONE>{C, bias, ldc}, (cudaStream_t)stream, 1, lda);
 }
 

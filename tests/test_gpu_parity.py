@@ -568,3 +568,24 @@ def test_pipelined_separator_equals_eager(cuda):
         assert torch.equal(a, e)
     # the geometry knobs are restored after every capture: an eager call afterwards is the lone-batch form again
     assert torch.equal(sep.separate(wavs[0], idxs[0]), eager[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('M,N,K,act', [(20480, 512, 200, 'none'), (19000, 2400, 600, 'none'), (30000, 300, 129, 'tanh')])
+def test_linear_tc_two_cta_tiles(cuda, M, N, K, act):
+    """Projections big enough for the 2-CTA (tcgen05.mma.cta_group::2, 256 x 256 tile per SM pair) kernel -- row counts that are
+    not a multiple of 256 (partial pair, partial CTA), output widths that leave half of a W tile empty, K with a partial
+    k-block -- against float64."""
+    import dl4ss_b200 as d
+    from dl4ss_b200 import modules as Mo
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    if act == 'tanh':
+        ref = torch.tanh(ref)
+    got = Mo.linear_tc(Mo.split_bf16(x.to(cuda)), Mo.split_bf16(w.to(cuda)), b.to(cuda), M, N, K, act=act).cpu()
+    err = (got.double() - ref).abs().max().item()
+    pre = (x.double() @ w.double().t() + b.double()).abs().max().item()          # bf16x3: ~1e-5 of the pre-activation scale
+    assert err < 2e-5 * max(1.0, pre), err
