@@ -411,7 +411,8 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                 }
                 if (ovalid) {
                     const int b = row0 + oc;
-                    *reinterpret_cast<float4 *>(p.y + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + uq) = make_float4(ho[0], ho[1], ho[2], ho[3]);
+                    if (p.y != nullptr)      // inference with planes: nobody reads the fp32 copy (half of the layer's output bytes)
+                        *reinterpret_cast<float4 *>(p.y + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + uq) = make_float4(ho[0], ho[1], ho[2], ho[3]);
                     if (p.y_planes != nullptr) {
                         const size_t o = ((size_t)b * T + t) * p.Kpy + (size_t)dir * H + uq;
                         *reinterpret_cast<uint2 *>(p.y_planes + o) = phi;
@@ -572,7 +573,7 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
                                       void *y_planes, float *hmean_out,
                                       void *workspace, size_t workspace_bytes, void *stream) {
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_tc_fwd: bad cell %d", cell);
-    DL4SS_CHECK_ARG(xproj && whh_planes && y, "rnn_layer_tc_fwd: null operand");
+    DL4SS_CHECK_ARG(xproj && whh_planes && (y || y_planes), "rnn_layer_tc_fwd: null operand (y may be NULL only when y_planes is given)");
     DL4SS_CHECK_ARG((((uintptr_t)xproj) & 15) == 0, "rnn_layer_tc_fwd: xproj must be 16-byte aligned");
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || bhn, "rnn_layer_tc_fwd: GRU needs bhn");
     DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1, "rnn_layer_tc_fwd: bad B/T/H %d/%d/%d", B, T, H);

@@ -223,10 +223,12 @@ def whh_planes(lw, cell, H):
     return pl
 
 
-def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None, y=None, y_planes=None, hmean=None):
-    """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]."""
+def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None, y=None, y_planes=None, hmean=None,
+                    want_y=True):
+    """K3: one bidirectional layer over the hoisted input projection xproj [B*T, 2*G*H] -> y [B,T,2H]
+    (want_y=False with y_planes on the tcgen05 kernel: planes only, returns None)."""
     lib = _lib.load()
-    if y is None:
+    if y is None and (want_y or y_planes is None or tc_rec is not True):
         y = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
     if tc_rec == 'mma':
         rc = lib.dl4ss_rnn_layer_mma_fwd(cell, _lib.ptr(xproj), _lib.ptr(lw['whh']), _lib.ptr(lw['bhn']),
@@ -247,7 +249,17 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     return y
 
 
-def rnn_forward(packed, x, save=None, buffers=None, extras=None):
+class HiddenStub(object):
+    """Shape / device of an encoder output that was produced as bf16 planes only (`rnn_forward(..., need_y=False)`)."""
+
+    def __init__(self, shape, device):
+        self.shape, self.device = torch.Size(shape), device
+
+    def view(self, *a):
+        raise RuntimeError('the encoder output exists as bf16 planes only (extras["planes"]); call encode() without planes_only')
+
+
+def rnn_forward(packed, x, save=None, buffers=None, extras=None, need_y=True):
     """Bidirectional multi-layer LSTM/GRU forward, batch_first, zero initial state.
     x [B,T,in] -> y [B,T,2H].  `save` (list) receives per-layer tensors for backward; `buffers` (list of dicts
     with 'y', 'gates', 'cells' per layer) makes the layers write into caller-owned static tensors; `extras` (dict)
@@ -275,9 +287,8 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None):
     for li, lw in enumerate(layers):
         a_pl = None
         if use_tensor_cores():
-            x2d = inp.view(B * T, -1)
-            a_pl = planes if planes is not None else split_bf16(x2d)
-            linear_tc(a_pl, weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
+            a_pl = planes if planes is not None else split_bf16(inp.view(B * T, -1))
+            linear_tc(a_pl, weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, inp.shape[-1], out=xproj)
         else:
             linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
         gates = cells = y_out = None
@@ -293,8 +304,11 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None):
                 planes[:, :, 2 * H:].zero_()    # the kernel writes columns [0, 2H)
             if li == len(layers) - 1:
                 hmean = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
+        skip_y = fuse and not need_y and save is None and buffers is None
         y = recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates, cells, y_out, planes,
-                            hmean if li == len(layers) - 1 else None)
+                            hmean if li == len(layers) - 1 else None, want_y=not skip_y)
+        if y is None:
+            y = HiddenStub((B, T, 2 * H), dev)
         if save is not None:
             save.append({'x': inp, 'y': y, 'gates': gates, 'cells': cells,
                          'x_planes': a_pl if use_tensor_cores() else None, 'y_planes': planes})
@@ -453,8 +467,10 @@ class MIX_SPEECH(nn.Module):
         self.Linear = nn.Linear(2 * config.HIDDEN_UNITS, self.input_fre * config.EMBEDDING_SIZE)
         self._packed = _PackedRNN(self.layer)
 
-    def encode(self, x, extras=None):
-        return rnn_forward(self._packed, x, extras=extras)
+    def encode(self, x, extras=None, planes_only=False):
+        """x [B,T,F] -> hidden [B,T,2H].  planes_only (needs `extras`): on the fused tensor-core path the layers emit bf16 planes
+        only (extras['planes'], extras['hmean']) and a `HiddenStub` with the shape is returned -- what `Separator` consumes."""
+        return rnn_forward(self._packed, x, extras=extras, need_y=not (planes_only and extras is not None))
 
     def forward(self, x):
         B, T, F = x.shape

@@ -49,7 +49,12 @@ class Separator(object):
     def masks(self, mix_feas, spk_idx, check_index=True):
         """mix_feas [B,T,F], spk_idx int [B,S] -> masks [B,S,T,F] (cRM: decompressed [B,S,T,F,2])."""
         extras = {}
-        hidden = self.mix.encode(mix_feas, extras)
+        lin = self.mix.Linear
+        S = spk_idx.shape[1] if hasattr(spk_idx, 'shape') else len(spk_idx[0])
+        # the fused Linear/tanh/attention kernel (E = 50, S <= 4) reads the encoder output as bf16 planes and ADDJUST its fused
+        # T-mean: the fp32 copy of the hidden states is then never read and the recurrent kernel does not write it
+        fused_head = M.use_tensor_cores() and lin.out_features // self.mix.input_fre == 50 and S <= 4
+        hidden = self.mix.encode(mix_feas, extras, planes_only=fused_head)
         return self.masks_from_hidden(hidden, extras, spk_idx, check_index)
 
     def masks_from_hidden(self, hidden, extras, spk_idx, check_index=True):

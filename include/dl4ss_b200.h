@@ -142,7 +142,9 @@ size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
 /* Optional fused outputs (NULL to skip): y_planes = y already split into bf16 hi/lo planes
  * [2][B*T][Kp], Kp = 2H rounded up to 64, for the next dl4ss_linear_tc_fwd / dl4ss_emb_attn_mask_tc_fwd (the
  * kernel writes columns [0,2H); the caller keeps the padding columns zero); hmean_out [B,2H] = mean over T of
- * y, the ADDJUST input (pass it to dl4ss_speaker_query_fwd as h with T = 1). */
+ * y, the ADDJUST input (pass it to dl4ss_speaker_query_fwd as h with T = 1).  * y may be NULL when y_planes is given: the layer's output then leaves as bf16 hi/lo planes only (the operand form of the next
+ * projection), half of the output bytes -- the inference pipeline reads nothing else.
+ */
 int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *whh_planes, const float *bhn,
                            float *y, int B, int T, int H, float *gates_save, float *cell_save,
                            void *y_planes, float *hmean_out,
