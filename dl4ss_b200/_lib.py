@@ -36,6 +36,8 @@ SIGNATURES = {
     'dl4ss_rnn_tc_set_trace': (None, [c_p, c_i]),
     'dl4ss_rnn_tc_set_tiles_per_cta': (None, [c_i]),
     'dl4ss_gemm_tc_set_max_ctas': (None, [c_i]),
+    'dl4ss_gemm_tc_set_two_cta': (None, [c_i]),
+    'dl4ss_rnn_tc_set_cluster_pairs': (None, [c_i]),
     'dl4ss_rnn_tc_whh_bytes': (c_sz, [c_i]),
     'dl4ss_rnn_tc_pack_whh': (c_i, [c_i, c_p, c_i, c_p, c_p]),
     'dl4ss_rnn_tc_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),

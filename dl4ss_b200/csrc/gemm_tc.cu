@@ -756,6 +756,7 @@ static int make_mn_map(CUtensorMap *map, const void *planes, int cols, int ld, i
 using namespace dl4ss;
 
 extern "C" void dl4ss_gemm_tc_set_max_ctas(int ctas) { g_max_ctas = ctas; }
+extern "C" void dl4ss_gemm_tc_set_two_cta(int mode) { g_two_cta = mode; }
 
 extern "C" size_t dl4ss_split_bf16_bytes(long long R, int K) {
     if (R <= 0 || K <= 0) return 0;

@@ -471,6 +471,7 @@ pack_whh_kernel(const float *__restrict__ whh, int G, int H, int Kp, __nv_bfloat
 
 static long long *g_trace = nullptr;
 static int g_trace_steps = 0;
+static int g_cluster_pairs = [] { const char *e = getenv("DL4SS_RNN_CLUSTER_PAIRS"); return e ? atoi(e) : 0; }();
 static int g_tiles_per_cta = [] { const char *e = getenv("DL4SS_RNN_TILES_PER_CTA"); return e ? atoi(e) : 0; }();
 
 template <int CELL>
@@ -516,7 +517,25 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int tiles_left, 
         if (rc) return rc;
     }
     void *args[] = {(void *)&mh, (void *)&mx, (void *)&p};
-    DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * ngroups * p.nslices), dim3(RT_THREADS), args, smem, st));
+    if (g_cluster_pairs) {
+        // placement only: as 2-CTA clusters the launch packs TPCs (60 CTAs on 30 TPCs instead of one SM of 60 TPCs), which leaves
+        // whole TPCs to a 2-CTA projection launch of the other in-flight batch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ngroups * p.nslices);
+        cfg.blockDim = dim3(RT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        DL4SS_CUDA(cudaLaunchKernelExC(&cfg, (const void *)kern, args));
+    } else {
+        DL4SS_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(2 * ngroups * p.nslices), dim3(RT_THREADS), args, smem, st));
+    }
     count_launch();
     return DL4SS_OK;
 }
@@ -534,6 +553,7 @@ extern "C" void dl4ss_rnn_tc_set_trace(void *dev_buf, int steps) {
 }
 
 extern "C" void dl4ss_rnn_tc_set_tiles_per_cta(int tiles) { g_tiles_per_cta = tiles; }
+extern "C" void dl4ss_rnn_tc_set_cluster_pairs(int on) { g_cluster_pairs = on; }
 
 extern "C" int dl4ss_rnn_tc_supported(int H, int cell) {
     return (cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU) && rnn_tc_supported(H) ? 1 : 0;

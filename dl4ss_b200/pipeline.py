@@ -134,6 +134,10 @@ class Separator(object):
         return preds, spk
 
 
+_ENV_TWO_CTA = int(__import__('os').environ.get('DL4SS_GEMM_2CTA', '1'))          # the library's own defaults (A/B switches)
+_ENV_PAIRS = int(__import__('os').environ.get('DL4SS_RNN_CLUSTER_PAIRS', '0'))
+
+
 class sm_sharing(object):
     """Launch geometry for batches that run side by side on different streams: the recurrent kernel packs `tiles`
     utterance tiles into every CTA (3 -> 60 CTAs for 256 utterances instead of 80) and a projection launch takes at
@@ -153,14 +157,22 @@ class sm_sharing(object):
 
     def __enter__(self):
         lib = _lib.load()
+        shared = self.want != (0, 0)
         lib.dl4ss_rnn_tc_set_tiles_per_cta(self.want[0])
         lib.dl4ss_gemm_tc_set_max_ctas(self.want[1])
+        # shared geometry: the recurrent launch as 2-CTA clusters (it then fills whole TPCs) and the plain projections on
+        # 2-CTA tiles under the cap as well (they need both SMs of a TPC): 6.70 -> 6.60 ms per step
+        if shared:
+            lib.dl4ss_rnn_tc_set_cluster_pairs(1)
+            lib.dl4ss_gemm_tc_set_two_cta(2 if _ENV_TWO_CTA else 0)
         return self
 
     def __exit__(self, *exc):
         lib = _lib.load()
         lib.dl4ss_rnn_tc_set_tiles_per_cta(0)
         lib.dl4ss_gemm_tc_set_max_ctas(0)
+        lib.dl4ss_rnn_tc_set_cluster_pairs(_ENV_PAIRS)
+        lib.dl4ss_gemm_tc_set_two_cta(_ENV_TWO_CTA)
         return False
 
 

@@ -136,6 +136,12 @@ void   dl4ss_rnn_tc_set_tiles_per_cta(int tiles);
  * occupy: 0 = one per SM; n = at most n, so that two pipelined batches on different streams share the SMs (a recurrent
  * launch of one batch next to a projection launch of the other).  Process-wide; initial value from DL4SS_GEMM_MAX_CTAS. */
 void   dl4ss_gemm_tc_set_max_ctas(int ctas);
+/* 2-CTA (tcgen05.mma.cta_group::2) form of the plain projections: 0 = never, 1 = when a launch owns the GPU (no CTA cap;
+ * default), 2 = also under a cap (cap / 2 CTA pairs).  Initial value from DL4SS_GEMM_2CTA. */
+void   dl4ss_gemm_tc_set_two_cta(int mode);
+/* launch dl4ss_rnn_layer_tc_fwd as 2-CTA clusters (placement only: its CTAs then fill whole TPCs, leaving whole TPCs to the
+ * 2-CTA projections of another in-flight batch).  Initial value from DL4SS_RNN_CLUSTER_PAIRS (default 0). */
+void   dl4ss_rnn_tc_set_cluster_pairs(int on);
 size_t dl4ss_rnn_tc_whh_bytes(int H);
 int    dl4ss_rnn_tc_pack_whh(int cell, const float *whh, int H, void *planes, void *stream);
 size_t dl4ss_rnn_tc_workspace_bytes(int B, int T, int H, int cell);
