@@ -711,14 +711,15 @@ static int g_two_cta = [] { const char *e = getenv("DL4SS_GEMM_2CTA"); return e 
 // batches in flight the recurrent launch of the other batch leaves single SMs free, not TPC pairs) and the output is at
 // least one 256-row tile pair per SM pair
 template <typename Epi>
-static int launch_tc2(const void *a_planes, const void *w_planes, int M, int N, int K, const Epi &epi, cudaStream_t st, int lda = 0) {
+static int launch_tc2(const void *a_planes, const void *w_planes, int M, int N, int K, const Epi &epi, cudaStream_t st, int lda = 0,
+                      int n_tiles_in = 0) {
     const int Kp = (K + TBK - 1) / TBK * TBK;
     CUtensorMap ma, mb;
     int rc = make_plane_map(&ma, a_planes, M, Kp, TBM, lda, lda > 0 ? K : 0);
     if (rc) return rc;
     rc = make_plane_map(&mb, w_planes, N, Kp, T2_BHALF);
     if (rc) return rc;
-    const int m_tiles2 = cdiv(M, 2 * TBM), n_tiles = cdiv(N, TBN);
+    const int m_tiles2 = cdiv(M, 2 * TBM), n_tiles = n_tiles_in > 0 ? n_tiles_in : cdiv(N, TBN);
     const long long total = (long long)m_tiles2 * n_tiles;
     int pairs = sm_count() / 2;
     if (g_max_ctas > 0 && g_max_ctas / 2 < pairs) pairs = g_max_ctas / 2;
@@ -880,5 +881,7 @@ extern "C" int dl4ss_emb_attn_mask_tc_fwd(const void *h_planes, const void *w_pl
     if (B == 0) return DL4SS_OK;
     DL4SS_CHECK_ARG((long long)B * T < (1ll << 31), "emb_attn_mask_tc_fwd: B*T too large");
     EpiAttn e{bias, q, mask_out, T, F, S, mode == DL4SS_ATT_DOT_CRM ? 1 : 0, crm_k, crm_c};
+    static const int attn2 = [] { const char *v = getenv("DL4SS_ATTN_2CTA"); return v ? atoi(v) : 1; }();
+    if (attn2 && use_two_cta(B * T, F * E)) return launch_tc2(h_planes, w_planes, B * T, F * E, K, e, (cudaStream_t)stream, 0, cdiv(F, ATT_BINS));
     return launch_tc(h_planes, w_planes, B * T, F * E, K, cdiv(F, ATT_BINS), e, (cudaStream_t)stream);
 }
