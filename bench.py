@@ -849,7 +849,13 @@ def main():
             # two batches' recurrent launches run side by side in the timed region (60 SMs each): the GPU-level figure is
             # their joint work over their joint duration; the figure of one launch owning the GPU (80 SMs) is kept next to it
             conc = {'batches': 2, 'ctas_per_launch': 60, 'ms_all_layers': rec_conc,
-                    'single_launch_achieved': ach, 'single_launch_frac': ach / peaks['bf16_tflops_sustained']}
+                    'single_launch_achieved': ach, 'single_launch_frac': ach / peaks['bf16_tflops_sustained'],
+                    # strict per-launch reading: one batch's launches while the other batch's run beside them on the other SMs
+                    'per_launch_in_region_achieved': flops[dom] / (rec_conc * 1e-3) / 1e12,
+                    'per_launch_in_region_frac': flops[dom] / (rec_conc * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
+                    'explanation': 'achieved / frac above are GPU level: two batches\' recurrent launches (60 CTAs each) run side by side in the '
+                                   'timed region, so the GPU completes 2 x flops per ms_all_layers; single_launch_* is one launch owning the GPU '
+                                   '(80 CTAs), per_launch_in_region_* one of the two concurrent launches taken alone'}
             ach = 2 * flops[dom] / (rec_conc * 1e-3) / 1e12
         tr = ncu_traffic({'rnn_recurrent': 'rnn_tc_kernel', 'rnn_xproj': 'EpiPlain', 'emb_attn_mask': 'EpiAttn'}[dom])
         roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
