@@ -11,6 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 200 $CMD --graph 0 > gpurun_out/plain2.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'stft256|istft' -s 6 -c 2 -f -o gpurun_out/prof_stft_${TAG} $CMD --graph 0 > gpurun_out/ncu2.log 2>&1
 timeout 200 $CMD --graph 0 > gpurun_out/plain3.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'rnn_tc|gemm_bf16x3' -s 12 -c 3 -f -o gpurun_out/prof_rnn_${TAG} $CMD --graph 0 > gpurun_out/ncu3.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'rnn_tc|gemm2?_bf16x3' -s 12 -c 4 -f -o gpurun_out/prof_rnn_${TAG} $CMD --graph 0 > gpurun_out/ncu3.log 2>&1
 tail -n 2 gpurun_out/ncu1.log gpurun_out/ncu2.log gpurun_out/ncu3.log
 head -c 400 gpurun_out/bench_${TAG}.json
