@@ -277,3 +277,46 @@ def test_linear_tc_tn_matches_float64(cuda, B, T, Ca, Cb, col0_a, M, col0_b, N, 
     want = torch.einsum('btm,btn->mn', shifted(a, sa)[:, :, col0_a:col0_a + M].double(), shifted(b, sb)[:, :, col0_b:col0_b + N].double())
     err = (got - want).abs().max().item()
     assert err < 3e-5 * want.abs().max().item(), err
+
+
+@pytest.mark.gpu
+def test_attn_dot_bwd_planes_and_lda_projection(cuda):
+    """dl4ss_attn_dot_bwd_planes emits exactly the bf16 hi/lo split of what dl4ss_attn_dot_bwd writes in fp32 (same dq), in
+    the [2][B*T][ldp] layout; dl4ss_linear_tc_lda_fwd multiplies those planes (row pitch ldp, K = F*E not a multiple of 64)
+    with a weight to within bf16x3 accuracy of float64."""
+    import dl4ss_b200 as d
+    from dl4ss_b200 import _lib, modules as Mo
+    lib = _lib.load()
+    B, S, T, F, E = 3, 2, 7, 129, 50
+    g = torch.Generator(device='cuda').manual_seed(3)
+    emb = torch.tanh(torch.randn(B, T * F, E, device=cuda, generator=g))
+    q = torch.randn(B, S, E, device=cuda, generator=g) * 0.3
+    mask = torch.rand(B, S, T * F, device=cuda, generator=g)
+    dmask = torch.randn(B, S, T * F, device=cuda, generator=g)
+    dz = torch.empty_like(emb)
+    dq = torch.empty_like(q)
+    rc = lib.dl4ss_attn_dot_bwd(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(mask), _lib.ptr(dmask), B, S, T * F, E, _lib.ATT_DOT,
+                                10.0, 0.1, _lib.ptr(dz), _lib.ptr(dq), _lib.stream())
+    assert rc == 0
+    ldp = (F * E + 7) // 8 * 8
+    planes = torch.zeros(2, B * T, ldp, device=cuda, dtype=torch.bfloat16)
+    dq2 = torch.empty_like(q)
+    rc = lib.dl4ss_attn_dot_bwd_planes(_lib.ptr(emb), _lib.ptr(q), _lib.ptr(mask), _lib.ptr(dmask), B, S, T, F, E, _lib.ATT_DOT,
+                                       10.0, 0.1, _lib.ptr(planes, torch.bfloat16), ldp, _lib.ptr(dq2), _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    dz2d = dz.view(B * T, F * E)
+    hi = dz2d.to(torch.bfloat16)
+    lo = (dz2d - hi.float()).to(torch.bfloat16)
+    assert torch.equal(planes[0, :, :F * E], hi) and torch.equal(planes[1, :, :F * E], lo)
+    assert float(planes[:, :, F * E:].abs().max()) == 0.0
+    assert torch.allclose(dq, dq2, rtol=1e-5, atol=1e-6)          # atomics: summation order differs
+    # dh = dz W from the planes as they lie
+    K, N = F * E, 600
+    w = torch.randn(K, N, device=cuda, generator=g) / K ** 0.5            # [K, N]: dh = dz @ w
+    out = torch.empty(B * T, N, device=cuda)
+    rc = lib.dl4ss_linear_tc_lda_fwd(_lib.ptr(planes, torch.bfloat16), ldp, _lib.ptr(Mo.split_bf16(w.t().contiguous()), torch.bfloat16),
+                                     None, _lib.ptr(out), N, B * T, N, K, _lib.stream())
+    assert rc == 0
+    want = dz2d.double() @ w.double()
+    assert (out.double() - want).abs().max().item() < 3e-5 * max(1e-6, want.abs().max().item())
