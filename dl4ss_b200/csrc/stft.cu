@@ -152,7 +152,7 @@ __device__ __forceinline__ void stft_store_rows(const cx2 (&v)[16], int l16, int
     }
 }
 
-template <typename WavT, int FEAT, bool CPLX, bool H128>
+template <typename WavT, int FEAT, bool CPLX, int HDIV>   // HDIV = n_fft / hop when that is 2 or 4, else 0
 __global__ void __launch_bounds__(K1_THREADS)
 stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_per_utt, int n_items,
                const float *__restrict__ window, float eps, int conj, int pf_dist,
@@ -199,7 +199,7 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
     {
         const WavT *w = wav + (size_t)b * L;
         const int s0 = f0 * hop - NFFT / 2;
-        if (H128 && ok[3]) {
+        if (HDIV == 2 && ok[3]) {
             float h[5][8];
             if (s0 >= 0 && s0 + 5 * (NFFT / 2) <= L) {
 #pragma unroll
@@ -218,6 +218,22 @@ stft256_kernel(const WavT *__restrict__ wav, int L, int hop, int T, int tiles_pe
                 const int q = n2 >> 3, n = n2 & 7;
                 v[n2].re = pmul(make_float2(h[q][n], h[q + 2][n]), wv);          // frames f0, f2
                 v[n2].im = pmul(make_float2(h[q + 1][n], h[q + 3][n]), wv);      // frames f1, f3
+            }
+        } else if (HDIV == 4 && ok[3]) {
+            // hop 64: the four frames span 448 samples = 28 sixteen-sample columns; frame i, column n2 is column 4i + n2
+            float h[28];
+            if (s0 >= 0 && s0 + 7 * (NFFT / 4) <= L) {
+#pragma unroll
+                for (int k = 0; k < 28; ++k) h[k] = (float)w[s0 + 16 * k + l16];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 28; ++k) h[k] = load_reflect(w, s0 + 16 * k + l16, L);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const float2 wv = pbc(win[l16 + 16 * n2]);
+                v[n2].re = pmul(make_float2(h[n2], h[8 + n2]), wv);               // frames f0, f2
+                v[n2].im = pmul(make_float2(h[4 + n2], h[12 + n2]), wv);          // frames f1, f3
             }
         } else {
             const int sf[4] = {fr[0] * hop - NFFT / 2, fr[1] * hop - NFFT / 2, fr[2] * hop - NFFT / 2, fr[3] * hop - NFFT / 2};
@@ -705,6 +721,208 @@ istft_h128_kernel(const float *__restrict__ mask, const float2 *__restrict__ spe
     }
 }
 
+
+// ------------------------------------------------------------------------------------ K6, hop = n_fft/4
+// hop 64 (BASELINE configs[0], Torch_multi/config.py FRAME_SHIFT = 64): four frames cover every output sample.  A 16-lane group
+// inverse-transforms FOUR consecutive frames (4q .. 4q+3) of ONE source: the two packed complex transforms carry (f0, f1) and
+// (f2, f3).  Output sample j = 16a + l16 of a 64-sample block needs samples 64r + j of four different frames -- all of them
+// in registers of the SAME lane (sample 16*n1 + l16 sits in v[n1]) -- so the overlap-add is plain register arithmetic:
+//     block 4q+3 = f0[192+j] + f1[128+j] + f2[64+j] + f3[j]                       complete inside the group
+//     block 4q+4 = f1[192+j] + f2[128+j] + f3[64+j]           + next.f0[j]
+//     block 4q+5 = f2[192+j] + f3[128+j]                      + next.(f0[64+j] + f1[j])
+//     block 4q+6 = f3[192+j]                                  + next.(f0[128+j] + f1[64+j] + f2[j])
+// where the three `next` sums (192 floats) are parked by the following group in shared memory; the group after the tile's last
+// one is recomputed as halo.  Blocks are counted in padded samples (frame t starts at 64 t); output block k = padded block k + 2
+// (the n_fft/2 trim); frames outside [0, T) contribute nothing and the window sum-square envelope of the (at most two)
+// blocks they touch is summed from the frames that exist, as librosa.istft does.
+constexpr int K6Q_GROUPS = STFT_GROUPS - 1;      // output groups per CTA (the 16th is the halo)
+
+template <int MASK_KIND>
+__global__ void __launch_bounds__(STFT_THREADS, 2)
+istft_h64_kernel(const float *__restrict__ mask, const float2 *__restrict__ spec, int S, int T, int tiles_per_src,
+                 const float *__restrict__ window, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *xch = reinterpret_cast<float4 *>(smem_raw);                              // groups * 272
+    float2 *tw = reinterpret_cast<float2 *>(xch + STFT_GROUPS * DL4SS_XCH2_FLOAT4);  // 256
+    float *win = reinterpret_cast<float *>(tw + 256);                                // 256: w[n] / N
+    float *inv_full = win + NFFT;                                                    // 64: 1 / sum_r w^2[64 r + j]
+    // 71.3 KB in all.  Registers (126) hold it at two CTAs per SM: capping at 80 for three (24 warps) spills 150-270 bytes into
+    // the transform and measured 0.30 / 0.39 of the HBM peak instead of 0.47 / 0.58 (real / cRM masks).
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int tile = bid % tiles_per_src; bid /= tiles_per_src;
+    const int s = bid % S;
+    const int b = bid / S;
+    const int Lout = 64 * (T - 1);
+    const int g = tid >> 4, l16 = tid & 15;
+
+    tw[tid] = g_tw256[tid];
+    win[tid] = window[tid] * (1.0f / NFFT);
+    if (tid < 64) {
+        const float w0 = window[tid], w1 = window[tid + 64], w2 = window[tid + 128], w3 = window[tid + 192];
+        const float e = w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3;
+        inv_full[tid] = (e > 1.17549435e-38f) ? 1.0f / e : 1.0f;
+    }
+    __syncthreads();
+
+    const int q = tile * K6Q_GROUPS + g - 1;         // frames 4q .. 4q+3; q = -1 only parks nothing and outputs padded block 2
+    int fr[4];
+    bool fv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = 4 * q + i;
+        fv[i] = (t >= 0 && t < T);
+        fr[i] = min(max(t, 0), T - 1);               // clamped: loaded like any other frame, zeroed below
+    }
+    // warps whose groups hold no frame at all skip the transform (warp-uniform: both groups of a warp are tested)
+    const int q_lo = tile * K6Q_GROUPS + (g & ~1) - 1;
+    const bool warp_live = (4 * q_lo < T) && (4 * (q_lo + 1) + 3 >= 0);
+    cx2 v[16];
+    if (warp_live) {
+        // pa: masked spectra of frames (f0 | f2), pb: (f1 | f3), packed over the two transforms
+        cx2 pa[8], pb[8];
+        float2 pa_n = make_float2(0.f, 0.f), pb_n = make_float2(0.f, 0.f);
+        const size_t xrow = (MASK_KIND == DL4SS_MASK_NONE) ? ((size_t)b * S + s) * T : (size_t)b * T;
+        const float2 *x0 = spec + (xrow + fr[0]) * NBIN, *x1 = spec + (xrow + fr[1]) * NBIN;
+        const float2 *x2 = spec + (xrow + fr[2]) * NBIN, *x3 = spec + (xrow + fr[3]) * NBIN;
+        const size_t mrow = ((size_t)b * S + s) * T;
+        if (MASK_KIND == DL4SS_MASK_NONE) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2 a0 = x0[16 * m + l16], a1 = x1[16 * m + l16], a2 = x2[16 * m + l16], a3 = x3[16 * m + l16];
+                pa[m] = cx2{make_float2(a0.x, a2.x), make_float2(a0.y, a2.y)};
+                pb[m] = cx2{make_float2(a1.x, a3.x), make_float2(a1.y, a3.y)};
+            }
+            if (l16 == 0) {
+                pa_n = make_float2(x0[128].x, x2[128].x);
+                pb_n = make_float2(x1[128].x, x3[128].x);
+            }
+        } else if (MASK_KIND == DL4SS_MASK_REAL) {
+            const float *m0 = mask + (mrow + fr[0]) * NBIN, *m1 = mask + (mrow + fr[1]) * NBIN;
+            const float *m2 = mask + (mrow + fr[2]) * NBIN, *m3 = mask + (mrow + fr[3]) * NBIN;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2 a0 = x0[16 * m + l16], a1 = x1[16 * m + l16], a2 = x2[16 * m + l16], a3 = x3[16 * m + l16];
+                const float k0 = __ldcs(m0 + 16 * m + l16), k1 = __ldcs(m1 + 16 * m + l16);
+                const float k2 = __ldcs(m2 + 16 * m + l16), k3 = __ldcs(m3 + 16 * m + l16);
+                pa[m] = cx2{make_float2(k0 * a0.x, k2 * a2.x), make_float2(k0 * a0.y, k2 * a2.y)};
+                pb[m] = cx2{make_float2(k1 * a1.x, k3 * a3.x), make_float2(k1 * a1.y, k3 * a3.y)};
+            }
+            if (l16 == 0) {
+                pa_n = make_float2(m0[128] * x0[128].x, m2[128] * x2[128].x);
+                pb_n = make_float2(m1[128] * x1[128].x, m3[128] * x3[128].x);
+            }
+        } else {
+            const float2 *cm = reinterpret_cast<const float2 *>(mask);
+            const float2 *m0 = cm + (mrow + fr[0]) * NBIN, *m1 = cm + (mrow + fr[1]) * NBIN;
+            const float2 *m2 = cm + (mrow + fr[2]) * NBIN, *m3 = cm + (mrow + fr[3]) * NBIN;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2 a0 = x0[16 * m + l16], a1 = x1[16 * m + l16], a2 = x2[16 * m + l16], a3 = x3[16 * m + l16];
+                const float2 k0 = m0[16 * m + l16], k1 = m1[16 * m + l16], k2 = m2[16 * m + l16], k3 = m3[16 * m + l16];
+                // reference order: re = Mr*Xr - Mi*Xi ; im = Mr*Xi + Mi*Xr
+                pa[m] = cx2{make_float2(k0.x * a0.x - k0.y * a0.y, k2.x * a2.x - k2.y * a2.y),
+                            make_float2(k0.x * a0.y + k0.y * a0.x, k2.x * a2.y + k2.y * a2.x)};
+                pb[m] = cx2{make_float2(k1.x * a1.x - k1.y * a1.y, k3.x * a3.x - k3.y * a3.y),
+                            make_float2(k1.x * a1.y + k1.y * a1.x, k3.x * a3.y + k3.y * a3.x)};
+            }
+            if (l16 == 0) {
+                const float2 a0 = x0[128], a1 = x1[128], a2 = x2[128], a3 = x3[128];
+                const float2 k0 = m0[128], k1 = m1[128], k2 = m2[128], k3 = m3[128];
+                pa_n = make_float2(k0.x * a0.x - k0.y * a0.y, k2.x * a2.x - k2.y * a2.y);
+                pb_n = make_float2(k1.x * a1.x - k1.y * a1.y, k3.x * a3.x - k3.y * a3.y);
+            }
+        }
+        if (l16 == 0) {   // DC bin: irfft ignores the imaginary part
+            pa[0].im = make_float2(0.f, 0.f);
+            pb[0].im = make_float2(0.f, 0.f);
+        }
+        // Z[k] = A[k] + i*B[k] for k <= 128 ; Z[256-k] = conj(A[k]) + i*conj(B[k])
+        const int src = (16 - l16) & 15;
+        cx2 c[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            v[m] = cx2{psub(pa[m].re, pb[m].im), padd(pa[m].im, pb[m].re)};
+            c[m] = cx2{padd(pa[m].re, pb[m].im), psub(pb[m].re, pa[m].im)};
+        }
+#pragma unroll
+        for (int m = 8; m < 16; ++m) {
+            cx2 t;
+            t.re.x = __shfl_sync(0xffffffffu, c[15 - m].re.x, src, 16);
+            t.re.y = __shfl_sync(0xffffffffu, c[15 - m].re.y, src, 16);
+            t.im.x = __shfl_sync(0xffffffffu, c[15 - m].im.x, src, 16);
+            t.im.y = __shfl_sync(0xffffffffu, c[15 - m].im.y, src, 16);
+            if (l16 == 0) {
+                if (m == 8) t = cx2{pa_n, pb_n};
+                else t = c[16 - m];
+            }
+            v[m] = t;
+        }
+        fft256x2_group<true>(v, l16, xch + g * DL4SS_XCH2_FLOAT4, tw);
+        __syncwarp();     // the group's transpose buffer is reused below as its parking slot
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = cx2{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    }
+    // windowed samples 16*n1 + l16 of the four frames (absent frames: zero): f0 = re.x, f1 = im.x, f2 = re.y, f3 = im.y
+    const float z0 = fv[0] ? 1.f : 0.f, z1 = fv[1] ? 1.f : 0.f, z2 = fv[2] ? 1.f : 0.f, z3 = fv[3] ? 1.f : 0.f;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const float w = win[16 * n1 + l16];
+        v[n1].re.x *= w * z0; v[n1].im.x *= w * z1; v[n1].re.y *= w * z2; v[n1].im.y *= w * z3;
+    }
+    // park what this group's frames add to the previous group's three open blocks
+    float *ex = reinterpret_cast<float *>(xch + g * DL4SS_XCH2_FLOAT4);      // [3][64], the (now idle) transpose buffer
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int j = 16 * a + l16;
+        ex[j] = v[a].re.x;                                               // f0[j]
+        ex[64 + j] = v[4 + a].re.x + v[a].im.x;                          // f0[64+j] + f1[j]
+        ex[128 + j] = v[8 + a].re.x + v[4 + a].im.x + v[a].re.y;         // f0[128+j] + f1[64+j] + f2[j]
+    }
+    // consumed by the group before: __syncwarp inside a warp; across warps warp w-1 waits for warp w (named barriers)
+    const int warp = tid >> 5;
+    __syncwarp();
+    if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp + 1) : "memory");
+    if (warp < STFT_THREADS / 32 - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 2) : "memory");
+    if (g >= K6Q_GROUPS) return;
+
+    const float *nx = reinterpret_cast<const float *>(xch + (g + 1) * DL4SS_XCH2_FLOAT4);
+    float *o = out + ((size_t)b * S + s) * Lout;
+    // padded block pb = 4q+3+i, i = 0..3 -> output block k = pb - 2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pbk = 4 * q + 3 + i;
+        const int k = pbk - 2;
+        if (k < 0 || k > T - 2) continue;
+        // contributing frames pbk-3 .. pbk: all four exist in the interior
+        const bool full = (pbk - 3 >= 0) && (pbk <= T - 1);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int j = 16 * a + l16;
+            float acc;
+            if (i == 0) acc = v[12 + a].re.x + v[8 + a].im.x + v[4 + a].re.y + v[a].im.y;
+            else if (i == 1) acc = v[12 + a].im.x + v[8 + a].re.y + v[4 + a].im.y + nx[j];
+            else if (i == 2) acc = v[12 + a].re.y + v[8 + a].im.y + nx[64 + j];
+            else acc = v[12 + a].im.y + nx[128 + j];
+            float inv;
+            if (full) inv = inv_full[j];
+            else {
+                float e = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int t = pbk - r;
+                    if (t >= 0 && t < T) { const float wt = __ldg(window + 64 * r + j); e += wt * wt; }
+                }
+                inv = (e > 1.17549435e-38f) ? 1.0f / e : 1.0f;
+            }
+            // win holds w/N; librosa divides the overlap-added w*frame by sum w^2
+            K6_STORE(o + (size_t)k * 64 + j, acc * inv);
+        }
+    }
+}
+
 }  // namespace dl4ss
 
 #include "stft_staged.cuh"
@@ -778,12 +996,16 @@ extern "C" int dl4ss_stft_feat(const void *wav, int wav_dtype, int B, int L, int
 #define LAUNCH_K1(WT, FM, CP)                                                                                  \
     do {                                                                                                        \
         if (h128) {                                                                                             \
-            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            stft256_kernel<WT, FM, CP, true><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                      \
+            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            stft256_kernel<WT, FM, CP, 2><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                         \
+                (const WT *)wav, L, hop, T, tiles, (int)grid, window, eps, conj, pf_k1, feat_out, (float2 *)cplx_out);   \
+        } else if (hop == NFFT / 4) {                                                                           \
+            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            stft256_kernel<WT, FM, CP, 4><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                         \
                 (const WT *)wav, L, hop, T, tiles, (int)grid, window, eps, conj, pf_k1, feat_out, (float2 *)cplx_out);   \
         } else {                                                                                                \
-            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            stft256_kernel<WT, FM, CP, false><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                     \
+            DL4SS_CUDA(cudaFuncSetAttribute(stft256_kernel<WT, FM, CP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            stft256_kernel<WT, FM, CP, 0><<<(unsigned)grid_k1, K1_THREADS, smem, st>>>(                         \
                 (const WT *)wav, L, hop, T, tiles, (int)grid, window, eps, conj, pf_k1, feat_out, (float2 *)cplx_out);   \
         }                                                                                                       \
     } while (0)
@@ -866,6 +1088,27 @@ extern "C" int dl4ss_mask_istft(const float *mask, int mask_kind, const float *s
         else LAUNCH_H128(DL4SS_MASK_COMPLEX);
 #undef LAUNCH_H128
         DL4SS_LAUNCH_CHECK("istft_h128_kernel");
+        return DL4SS_OK;
+    }
+    if (hop == NFFT / 4 && T >= 4) {        // hop 64: four frames of one source per group, overlap-add in registers
+        { int rc = ensure_twiddles(st0); if (rc) return rc; }
+        const int qmax = (T - 3) / 4;                         // last group with an output block (4q+3 <= T)
+        const int ngroups = qmax + 2;                         // q = -1 .. qmax
+        const int tiles_q = cdiv(ngroups, K6Q_GROUPS);
+        const size_t smem_q = STFT_GROUPS * DL4SS_XCH2_FLOAT4 * sizeof(float4) + 256 * sizeof(float2) + (NFFT + 64) * sizeof(float);
+        const long long grid_q = (long long)B * S * tiles_q;
+        DL4SS_CHECK_ARG(grid_q < (1ll << 31), "mask_istft: grid too large");
+#define LAUNCH_H64(KIND)                                                                                        \
+        do {                                                                                                    \
+            DL4SS_CUDA(cudaFuncSetAttribute(istft_h64_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q)); \
+            istft_h64_kernel<KIND><<<(unsigned)grid_q, STFT_THREADS, smem_q, st0>>>(                            \
+                mask, (const float2 *)spec, S, T, tiles_q, window, wav_out);                                    \
+        } while (0)
+        if (mask_kind == DL4SS_MASK_NONE) LAUNCH_H64(DL4SS_MASK_NONE);
+        else if (mask_kind == DL4SS_MASK_REAL) LAUNCH_H64(DL4SS_MASK_REAL);
+        else LAUNCH_H64(DL4SS_MASK_COMPLEX);
+#undef LAUNCH_H64
+        DL4SS_LAUNCH_CHECK("istft_h64_kernel");
         return DL4SS_OK;
     }
     const int halo = (NFFT - 1) / hop;         // frames before the first block's own frame
