@@ -149,6 +149,107 @@ attn_dot_bwd_kernel(const float *__restrict__ emb, const float *__restrict__ q, 
     }
 }
 
+
+// Flat form for the planes output with an even E (every reference config: E = 50): a thread owns one (row, column pair);
+// 32 rows x E/2 pairs per pass, so consecutive threads read consecutive float2 of emb and write consecutive bf16x2 of both
+// planes -- no shared-memory tile, no row-per-thread phases.  The dq partial sums stay in registers over the CTA's
+// AF_PASSES passes and leave through one shared-memory reduction and S*NQ*E atomics per 32*AF_PASSES rows (the tiled kernel
+// above issues them per 128 rows and measured 2.85 ms at B = 256 -- 17 % of the HBM rate its 3.1 GB need).
+__device__ __forceinline__ unsigned bf2_bits(__nv_bfloat162 v) { return *reinterpret_cast<unsigned *>(&v); }
+constexpr int AF_THREADS = 768;   // 24 warps x 40 registers: two CTAs per SM
+constexpr int AF_RPP = 32;        // rows per pass (fewer when 32 * E/2 > AF_THREADS)
+constexpr int AF_PASSES = 16;     // passes per CTA
+
+template <int MODE, int SMAX>          // SMAX >= S speakers: sizes the register arrays
+__global__ void __launch_bounds__(AF_THREADS, (SMAX * (MODE == DL4SS_ATT_DOT_CRM ? 2 : 1) <= 2) ? 2 : 1)
+attn_dot_bwd_flat_kernel(const float *__restrict__ emb, const float *__restrict__ q, const float *__restrict__ mask,
+                         const float *__restrict__ dmask, int S, int TF, int E2, float crm_k, float crm_c,
+                         float *__restrict__ dq, __nv_bfloat16 *__restrict__ planes, int F, int ldp,
+                         size_t plane_elems, size_t row_base) {
+    constexpr int NQ = (MODE == DL4SS_ATT_DOT_CRM) ? 2 : 1;
+    constexpr int NEMAX = SMAX * NQ;
+    extern __shared__ __align__(16) float2 red[];            // [S*NQ][AF_RPP][E2]
+    const int b = blockIdx.y;
+    const int rpp = blockDim.x / E2;                          // rows per pass
+    const int r0 = blockIdx.x * (rpp * AF_PASSES);
+    const int tid = threadIdx.x;
+    const int rl = tid / E2, e2 = tid - rl * E2;
+    const int NE = S * NQ;                                    // energies per row
+    const int E = 2 * E2, T = TF / F;
+
+    float2 qv[NEMAX], acc[NEMAX];
+#pragma unroll
+    for (int i = 0; i < NEMAX; ++i) {
+        acc[i] = make_float2(0.f, 0.f);
+        // q layout [S][NQ*E]: energy i = s*NQ + c at i*E
+        qv[i] = (i < NE) ? reinterpret_cast<const float2 *>(q + ((size_t)b * NE + i) * E)[e2] : make_float2(0.f, 0.f);
+    }
+    const float2 *src = reinterpret_cast<const float2 *>(emb) + (size_t)b * TF * E2;
+    constexpr int U = 4;                                      // passes whose loads are issued together
+    for (int k0 = 0; k0 < AF_PASSES; k0 += U) {
+        float2 xs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tf = r0 + (k0 + u) * rpp + rl;
+            xs[u] = (tf < TF) ? __ldcs(src + (size_t)tf * E2 + e2) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tf = r0 + (k0 + u) * rpp + rl;
+            if (tf >= TF) continue;
+            const float2 x = xs[u];
+            float dzx = 0.f, dzy = 0.f;
+#pragma unroll
+            for (int s_ = 0; s_ < SMAX; ++s_) {
+                if (s_ >= S) break;
+                const size_t j = ((size_t)b * S + s_) * TF + tf;
+                if (MODE == DL4SS_ATT_DOT) {
+                    const float m = __ldg(mask + j);
+                    const float d = __ldg(dmask + j) * m * (1.0f - m);
+                    dzx = fmaf(d, qv[s_].x, dzx); dzy = fmaf(d, qv[s_].y, dzy);
+                    acc[s_].x = fmaf(d, x.x, acc[s_].x); acc[s_].y = fmaf(d, x.y, acc[s_].y);
+                } else {
+                    const float2 m = __ldg(reinterpret_cast<const float2 *>(mask) + j);
+                    const float2 g = __ldg(reinterpret_cast<const float2 *>(dmask) + j);
+                    float d0, d1;
+                    if (crm_c > 0.f) { d0 = g.x * (2.0f / crm_c); d1 = g.y * (2.0f / crm_c); }
+                    else { d0 = g.x * (crm_k - m.x * m.x / crm_k); d1 = g.y * (crm_k - m.y * m.y / crm_k); }
+                    constexpr int LAST = NEMAX - 1;
+                    const int i0 = (2 * s_) & LAST, i1 = (2 * s_ + 1) & LAST;     // (& LAST: keeps the dead MODE's indices in range)
+                    dzx = fmaf(d0, qv[i0].x, dzx); dzy = fmaf(d0, qv[i0].y, dzy);
+                    dzx = fmaf(d1, qv[i1].x, dzx); dzy = fmaf(d1, qv[i1].y, dzy);
+                    acc[i0].x = fmaf(d0, x.x, acc[i0].x); acc[i0].y = fmaf(d0, x.y, acc[i0].y);
+                    acc[i1].x = fmaf(d1, x.x, acc[i1].x); acc[i1].y = fmaf(d1, x.y, acc[i1].y);
+                }
+            }
+            const float v0 = dzx * (1.0f - x.x * x.x), v1 = dzy * (1.0f - x.y * x.y);
+            const int t = tf / F, f = tf - t * F;
+            const size_t o = (row_base + (size_t)b * T + t) * ldp + (size_t)f * E + 2 * e2;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            __stcs(reinterpret_cast<unsigned *>(planes + o), bf2_bits(__halves2bfloat162(h0, h1)));
+            __stcs(reinterpret_cast<unsigned *>(planes + plane_elems + o),
+                   bf2_bits(__halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)))));
+        }
+    }
+    // dq[i][e] = sum over the CTA's rows: registers -> [i][row lane][pair] -> one thread per (i, pair)
+#pragma unroll
+    for (int i = 0; i < NEMAX; ++i)
+        if (i < NE) red[(i * rpp + rl) * E2 + e2] = acc[i];
+    __syncthreads();
+    if (tid < NE * E2) {
+        const int i = tid / E2, e = tid - i * E2;
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < rpp; ++r) {
+            const float2 v = red[(i * rpp + r) * E2 + e];
+            a.x += v.x; a.y += v.y;
+        }
+        float *d = dq + ((size_t)b * NE + i) * E + 2 * e;
+        atomicAdd(d, a.x);
+        atomicAdd(d + 1, a.y);
+    }
+}
+
 // ----------------------------------------------------------------------------------------- BPTT step
 template <int CELL>
 __global__ void __launch_bounds__(256)
@@ -242,6 +343,30 @@ static int attn_dot_bwd_impl(const float *emb, const float *q, const float *mask
     if (smem > 200 * 1024) {
         set_error("attn_dot_bwd: E=%d S=%d needs %zu B of shared memory", E, S, smem);
         return DL4SS_EUNSUPPORTED;
+    }
+    if (planes && (E & 1) == 0 && E <= 64) {
+        const int E2 = E / 2, NE = S * NQ;
+        const int rpp = (AF_RPP * E2 <= AF_THREADS) ? AF_RPP : AF_THREADS / E2;
+        const size_t smem2 = (size_t)NE * rpp * E2 * sizeof(float2);
+        for (int b0 = 0; b0 < B; b0 += 65535) {
+            const int nb = (B - b0 < 65535) ? B - b0 : 65535;
+            dim3 grid(cdiv(TF, rpp * AF_PASSES), nb);
+            const size_t mo = (size_t)b0 * S * TF * NQ;
+            const size_t plane_elems = (size_t)B * (TF / F) * ldp;
+            const size_t row_base = (size_t)b0 * (TF / F);
+#define LAUNCH_AF(MODE, SM)                                                                                      \
+            do {                                                                                                 \
+                DL4SS_CUDA(cudaFuncSetAttribute(attn_dot_bwd_flat_kernel<MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+                attn_dot_bwd_flat_kernel<MODE, SM><<<grid, rpp * E2, smem2, st>>>(emb + (size_t)b0 * TF * E,  \
+                    q + (size_t)b0 * NE * E, mask + mo, dmask + mo, S, TF, E2, crm_k, crm_c, dq + (size_t)b0 * NE * E, \
+                    planes, F, ldp, plane_elems, row_base);                                                      \
+            } while (0)
+            if (mode == DL4SS_ATT_DOT) { if (S <= 2) LAUNCH_AF(DL4SS_ATT_DOT, 2); else if (S <= 4) LAUNCH_AF(DL4SS_ATT_DOT, 4); else LAUNCH_AF(DL4SS_ATT_DOT, 8); }
+            else { if (S <= 2) LAUNCH_AF(DL4SS_ATT_DOT_CRM, 2); else LAUNCH_AF(DL4SS_ATT_DOT_CRM, 4); }
+#undef LAUNCH_AF
+            DL4SS_LAUNCH_CHECK("attn_dot_bwd_flat_kernel");
+        }
+        return DL4SS_OK;
     }
     for (int b0 = 0; b0 < B; b0 += 65535) {
         const int nb = (B - b0 < 65535) ? B - b0 : 65535;
