@@ -103,6 +103,7 @@ struct EpiPlain {
     float *C;
     const float *bias;
     int ldc;
+    int tr = 0;          // ATOMIC only: the tile is the transpose of what C holds -- element (m, n) is added to C[n * ldc + m]
 };
 struct EpiAttn {
     const float *bias;   // [F*E]
@@ -151,6 +152,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiPlain<ACT, ATOMIC> &e, ui
         tmem_ld16(taddr + cc * 32 + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
         const int n = n0 + cc * 32;
         if (n >= N) continue;                                                      // warp-uniform
+        if (ATOMIC && e.tr) {
+            // transposed output: TMEM's one-row-per-lane form is already the coalesced one (32 lanes = 32 consecutive m)
+            const int m = m_base + lane;
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < N) atomicAdd(e.C + (size_t)(n + j) * e.ldc + m, v[j]);
+            }
+            continue;
+        }
         __syncwarp();                                                              // the previous chunk's readers are done
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * TC_STAGE_PITCH + j] = v[j];
@@ -808,6 +819,14 @@ extern "C" int dl4ss_linear_tc_tn_splitk_fwd(const void *a_planes, int lda, int 
     cudaStream_t st = (cudaStream_t)stream;
     DL4SS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));   // the K splits meet in C through fp32 atomics
     if (B == 0) return DL4SS_OK;
+    static const bool g_mn_swap = [] { const char *e = getenv("DL4SS_MN_SWAP"); return !(e && e[0] == '0'); }();
+    // C = A^T B or, when that pads fewer tiles (M is cut in 128s, N in 256s: 1200 x 600 is 30 tiles one way, 25 the other;
+    // 1200 x 300 is 20 against 15), C^T = B^T A with the epilogue adding the tile transposed into the same C
+    const bool swap = (long long)cdiv(N, TBM) * cdiv(M, TBN) < (long long)cdiv(M, TBM) * cdiv(N, TBN) && g_mn_swap;
+    if (swap) {
+        std::swap(a_planes, b_planes); std::swap(lda, ldb); std::swap(wa, wb); std::swap(col0_a, col0_b);
+        std::swap(shift_a, shift_b); std::swap(M, N);
+    }
     CUtensorMap ma, mb;
     int rc = make_mn_map(&ma, a_planes, wa, lda, B, T);
     if (rc) return rc;
@@ -824,7 +843,7 @@ extern "C" int dl4ss_linear_tc_tn_splitk_fwd(const void *a_planes, int lda, int 
     auto kern = gemm_bf16x3_kernel<EpiPlain<DL4SS_ACT_NONE, true>, true>;
     DL4SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, M, N, kblocks, m_tiles, n_tiles, ns, sched_pair(st),
-                                            EpiPlain<DL4SS_ACT_NONE, true>{C, nullptr, ldc}, MnMode{tchunks, shift_a, shift_b, col0_a, col0_b});
+                                            EpiPlain<DL4SS_ACT_NONE, true>{C, nullptr, ldc, swap ? 1 : 0}, MnMode{tchunks, shift_a, shift_b, col0_a, col0_b});
     DL4SS_LAUNCH_CHECK("gemm_bf16x3_kernel<MN>");
     return DL4SS_OK;
 }

@@ -242,7 +242,8 @@ def test_pit_training_gradients(cuda):
 @pytest.mark.parametrize('B,T,Ca,Cb,col0_a,M,col0_b,N,sa,sb', [(3, 70, 200, 129, 0, 200, 0, 129, 0, 0),
                                                                (5, 313, 2400, 600, 1200, 1200, 300, 300, 0, 1),
                                                                (4, 64, 320, 600, 0, 300, 0, 300, 0, -1),
-                                                               (2, 130, 136, 72, 8, 100, 3, 60, 1, 0)])
+                                                               (2, 130, 136, 72, 8, 100, 3, 60, 1, 0),
+                                                               (2, 100, 1208, 608, 8, 1200, 0, 601, -1, 0)])   # swapped operands, transposed epilogue
 def test_linear_tc_tn_matches_float64(cuda, B, T, Ca, Cb, col0_a, M, col0_b, N, sa, sb):
     """MN-major split-K product (dl4ss_linear_tc_tn_splitk_fwd): sum over (b,t) of A[b,t+sa,col0_a+m] * B[b,t+sb,col0_b+n]
     from row-major bf16 hi/lo planes, against float64 -- column windows, frame shifts (out-of-range frames are zeros),
