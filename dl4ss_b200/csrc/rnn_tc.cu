@@ -63,6 +63,11 @@ struct RnnTcParams {
     int tile0, ntiles, tpg, ngroups, tiles_total, nslices;    // this launch: tiles [tile0, tile0+ntiles), tpg per CTA
     long long *trace;          // optional [steps][16] clock stamps of CTA 0 (profiling hook), else null
     int trace_steps;
+    // yx: the group exchanges h through y_planes itself (row (b, t-1) of the layer output IS h_{t-1}) instead of a separate
+    // ping-pong buffer: one set of publish stores per step instead of two.  A TMA box has to start on a 16-byte boundary, so
+    // the reverse direction's window starts hshift = H % 8 columns early (column H - hshift) and its resident W_hh rows are
+    // shifted by as many k positions (zeros in front); the <= 12 foreign columns either window touches meet zero weights.
+    int yx, hshift;
 };
 
 // xproj is read exactly once: evict-first in L2, so that the 769 MB stream does not displace the layer's own output
@@ -181,12 +186,22 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
         const int r = 32 * warp + lane;
         const bool rvalid = u0 + (r >> 2) < H;
         const uint32_t ta = tmem_base + ((uint32_t)(32 * warp) << 16) + RT_WCOL;
+        const bool shifted = p.yx && dir == 1 && p.hshift == 4;       // k' = k + 4 (hshift is 0 or 4: H % 4 == 0)
         for (int pl = 0; pl < 2; ++pl) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(
-                p.wplanes + ((size_t)pl * 8 * H + (size_t)dir * 4 * H + 4 * u0 + (rvalid ? r : 0)) * p.Kp);
+            const __nv_bfloat16 *row = p.wplanes + ((size_t)pl * 8 * H + (size_t)dir * 4 * H + 4 * u0 + (rvalid ? r : 0)) * p.Kp;
+            const uint4 *src = reinterpret_cast<const uint4 *>(row);
+            const uint2 *src2 = reinterpret_cast<const uint2 *>(row);       // 4 k positions each
             for (int kk = 0; kk < p.Kp / 16; ++kk) {
                 uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-                if (rvalid) { a = __ldg(src + 2 * kk); b = __ldg(src + 2 * kk + 1); }
+                if (rvalid) {
+                    if (!shifted) { a = __ldg(src + 2 * kk); b = __ldg(src + 2 * kk + 1); }
+                    else {
+                        const uint2 z = make_uint2(0u, 0u);
+                        const uint2 q0 = kk ? __ldg(src2 + 4 * kk - 1) : z, q1 = __ldg(src2 + 4 * kk);
+                        const uint2 q2 = __ldg(src2 + 4 * kk + 1), q3 = __ldg(src2 + 4 * kk + 2);
+                        a = make_uint4(q0.x, q0.y, q1.x, q1.y); b = make_uint4(q2.x, q2.y, q3.x, q3.y);
+                    }
+                }
                 tmem_st8(ta + pl * RT_WPLANE + kk * 8, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
             }
         }
@@ -213,7 +228,9 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
             unsigned char *hs = Hsm + (size_t)tl * nkc * 2 * RT_HBLK;
             const uint32_t a_hi = tmem_base + RT_WCOL, a_lo = a_hi + RT_WPLANE;
             const uint32_t d = tmem_base + tl * RT_TCOLS;
-            const int last_ksteps = (H - (nkc - 1) * RT_KC + 15) / 16;
+            const int hsh = (p.yx && dir == 1) ? p.hshift : 0;
+            const int last_ksteps = (H + hsh - (nkc - 1) * RT_KC + 15) / 16;
+            const int ycol0 = dir * H - hsh;                          // yx: first column of this direction's window in y_planes
             const unsigned per_step = (unsigned)p.nslices;            // one release per slice CTA and step
             const unsigned *ctr = counters + tl * RT_CTR_STRIDE;
             // the hoisted input projection of step s: ONE 5-D TMA box [32 utterances][G gates][32 units] (fp32, evict-first:
@@ -237,8 +254,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                 fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
                 for (int c = 0; c < nkc; ++c) {
                     mbar_expect_tx(&hfull[tl * RT_MAXKC + c], 2 * RT_HBLK);     // one box = both planes of the chunk
-                    tma_load_3d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], c * RT_KC,
-                                (tile_first + tl) * RT_NT, z);
+                    if (p.yx)       // rows (b, t of step s-1) of the layer output: [64 columns][1 frame][32 utterances][2 planes]
+                        tma_load_4d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], ycol0 + c * RT_KC,
+                                    dir ? (T - s) : (s - 1), (tile_first + tl) * RT_NT, 0);
+                    else
+                        tma_load_3d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], c * RT_KC,
+                                    (tile_first + tl) * RT_NT, z);
                 }
                 if (tl == 0) stamp(p, s, 2);
                 if (s >= 2) { mbar_wait(&tempty[tl], (uint32_t)(s - 2) & 1u); tc_fence_after(); }
@@ -384,8 +405,13 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                 }
                 const uint2 phi = make_uint2(pack_bf16x2(hhi[0], hhi[1]), pack_bf16x2(hhi[2], hhi[3]));
                 const uint2 plo = make_uint2(pack_bf16x2(hlo[0], hlo[1]), pack_bf16x2(hlo[2], hlo[3]));
+                if (p.yx && ovalid) {       // the layer output row is the publish
+                    const size_t o = ((size_t)(row0 + oc) * T + t) * p.Kpy + (size_t)dir * H + uq;
+                    *reinterpret_cast<uint2 *>(p.y_planes + o) = phi;
+                    *reinterpret_cast<uint2 *>(p.y_planes + (size_t)p.B * T * p.Kpy + o) = plo;
+                }
                 if (s + 1 < T) {
-                    if (ovalid) {
+                    if (ovalid && !p.yx) {
                         const int pp = s & 1;
                         __nv_bfloat16 *hh = p.hbuf + ((size_t)((pp * 2 + dir) * 2) * p.Bpad + row0 + oc) * p.Kp + uq;
                         *reinterpret_cast<uint2 *>(hh) = phi;
@@ -413,7 +439,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                     const int b = row0 + oc;
                     if (p.y != nullptr)      // inference with planes: nobody reads the fp32 copy (half of the layer's output bytes)
                         *reinterpret_cast<float4 *>(p.y + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + uq) = make_float4(ho[0], ho[1], ho[2], ho[3]);
-                    if (p.y_planes != nullptr) {
+                    if (p.y_planes != nullptr && !p.yx) {
                         const size_t o = ((size_t)b * T + t) * p.Kpy + (size_t)dir * H + uq;
                         *reinterpret_cast<uint2 *>(p.y_planes + o) = phi;
                         *reinterpret_cast<uint2 *>(p.y_planes + (size_t)p.B * T * p.Kpy + o) = plo;
@@ -469,9 +495,23 @@ pack_whh_kernel(const float *__restrict__ whh, int G, int H, int Kp, __nv_bfloat
     }
 }
 
+// zero columns [c0, c1) and [c2, Kpy) of every row of the planes (all multiples of 8 columns: whole 16-byte pieces)
+__global__ void __launch_bounds__(256)
+zero_plane_cols_kernel(__nv_bfloat16 *planes, long long rows, int Kpy, int c0, int c1, int c2) {
+    const int n1 = (c1 - c0) >> 3, n2 = (Kpy - c2) >> 3, per = n1 + n2;
+    const long long total = rows * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per;
+        const int q = (int)(i - r * per);
+        const int col = q < n1 ? c0 + 8 * q : c2 + 8 * (q - n1);
+        *reinterpret_cast<uint4 *>(planes + r * Kpy + col) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 static long long *g_trace = nullptr;
 static int g_trace_steps = 0;
 static int g_cluster_pairs = [] { const char *e = getenv("DL4SS_RNN_CLUSTER_PAIRS"); return e ? atoi(e) : 0; }();
+static int g_yx = [] { const char *e = getenv("DL4SS_RNN_YX"); return e ? atoi(e) : 1; }();
 static int g_tiles_per_cta = [] { const char *e = getenv("DL4SS_RNN_TILES_PER_CTA"); return e ? atoi(e) : 0; }();
 
 template <int CELL>
@@ -500,7 +540,13 @@ static int launch_rnn_tc(RnnTcParams p, const void *whh_planes, int tiles_left, 
 
     CUtensorMap mh;
     p.wplanes = (const __nv_bfloat16 *)whh_planes;
-    {   // h exchange bf16 [8 = pp,dir,plane][Bpad][Kp]: box = 64 k x 32 rows x both planes
+    if (p.yx) {   // the layer output planes bf16 [2][B][T][Kpy]: box = 64 columns x 1 frame x 32 utterances x both planes
+        cuuint64_t dims[4] = {(cuuint64_t)p.Kpy, (cuuint64_t)p.T, (cuuint64_t)p.B, 2};
+        cuuint64_t strides[3] = {(cuuint64_t)p.Kpy * 2, (cuuint64_t)p.T * p.Kpy * 2, (cuuint64_t)p.B * p.T * p.Kpy * 2};
+        cuuint32_t box[4] = {RT_KC, 1, RT_NT, 2};
+        int rc = make_bf16_map(&mh, p.y_planes, 4, dims, strides, box);
+        if (rc) return rc;
+    } else {   // h exchange bf16 [8 = pp,dir,plane][Bpad][Kp]: box = 64 k x 32 rows x both planes
         cuuint64_t dims[3] = {(cuuint64_t)p.Kp, (cuuint64_t)p.Bpad, 8};
         cuuint64_t strides[2] = {(cuuint64_t)p.Kp * 2, (cuuint64_t)p.Bpad * p.Kp * 2};
         cuuint32_t box[3] = {RT_KC, RT_NT, 2};
@@ -626,6 +672,20 @@ extern "C" int dl4ss_rnn_layer_tc_fwd(int cell, const float *xproj, const void *
     p.hbuf = (__nv_bfloat16 *)((unsigned char *)workspace + ctr);
     p.ntiles = p.tpg = p.ngroups = 0;
     p.trace = g_trace; p.trace_steps = g_trace_steps;
+    p.hshift = H % 8;
+    p.yx = (y_planes != nullptr && g_yx && (((uintptr_t)y_planes) & 15) == 0) ? 1 : 0;
+    if (p.yx) {
+        // the columns a direction's window shares with the other direction, the 16-wide k step's overhang and the row padding
+        // are read before anybody has written them: they meet zero weights, so they only have to be finite -- zeroed here
+        const int c0 = H - p.hshift, c1 = (H + 15) / 16 * 16 < p.Kpy ? (H + 15) / 16 * 16 : p.Kpy;
+        const long long rows = 2ll * B * T, total = rows * (((c1 - c0) >> 3) + ((p.Kpy - 2 * H) >> 3));
+        long long blocks = cdivll(total, 256);
+        if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+        if (total > 0) {            // H a multiple of 64: the windows are exact, nothing to zero
+            zero_plane_cols_kernel<<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16 *)y_planes, rows, p.Kpy, c0, c1, 2 * H);
+            DL4SS_LAUNCH_CHECK("zero_plane_cols_kernel");
+        }
+    }
     int t0 = 0;
     while (t0 < p.tiles_total) {
         p.tile0 = t0;

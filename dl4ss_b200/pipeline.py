@@ -144,7 +144,7 @@ class sm_sharing(object):
     most `gemm_ctas` SMs, so that the recurrent launch of one batch and a projection / recurrent launch of the other
     are co-resident.  The settings are process-wide in the library and read at launch time (a CUDA graph keeps the
     geometry it was captured with); (0, 0) = a lone batch owns the GPU."""
-    PIPELINED = (3, 88)
+    PIPELINED = tuple(int(v) for v in __import__('os').environ.get('DL4SS_SM_SHARING', '3,88').split(','))   # (tiles per recurrent CTA, projection CTA cap)
 
     @staticmethod
     def for_batch(B, inflight):
