@@ -17,6 +17,7 @@ library is missing.  Differences from the reference that do not change results: 
 the input (the reference reads config.BATCH_SIZE inside forward), and MIX_SPEECH may hand
 ATTENTION a `DeferredEmbedding` instead of the 8 MB/utterance [B,T,F,E] tensor (see below).
 """
+import os
 import numpy as np
 import torch
 from torch import nn
@@ -249,6 +250,9 @@ def recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, gates=None, cells=None
     return y
 
 
+_RNN_YX = os.environ.get('DL4SS_RNN_YX', '1') != '0'      # csrc/rnn_tc.cu: h exchanged through the output planes (the library's default)
+
+
 class HiddenStub(object):
     """Shape / device of an encoder output that was produced as bf16 planes only (`rnn_forward(..., need_y=False)`)."""
 
@@ -300,8 +304,8 @@ def rnn_forward(packed, x, save=None, buffers=None, extras=None, need_y=True):
         planes = None
         if fuse:
             planes = torch.empty(2, B * T, Kpy, device=dev, dtype=torch.bfloat16)
-            if Kpy > 2 * H:
-                planes[:, :, 2 * H:].zero_()    # the kernel writes columns [0, 2H)
+            if Kpy > 2 * H and not _RNN_YX:
+                planes[:, :, 2 * H:].zero_()    # the kernel writes columns [0, 2H) (and, exchanging h through the planes, zeroes the padding itself)
             if li == len(layers) - 1:
                 hmean = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
         skip_y = fuse and not need_y and save is None and buffers is None
