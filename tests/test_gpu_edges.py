@@ -19,11 +19,14 @@ def _rnn_pair(cell, layers, H, T, seed=1):
 
 
 @pytest.mark.parametrize('cell,H,B,T', [('lstm', 100, 5, 9), ('gru', 200, 33, 7), ('lstm', 320, 4, 6), ('lstm', 300, 257, 4),
-                                         ('gru', 300, 65, 3), ('lstm', 300, 1, 1), ('lstm', 60, 3, 5), ('gru', 90, 2, 5)])
+                                         ('gru', 300, 65, 3), ('lstm', 300, 1, 1), ('lstm', 60, 3, 5), ('gru', 90, 2, 5),
+                                         ('lstm', 296, 3, 5), ('gru', 316, 2, 4), ('lstm', 4, 2, 3), ('lstm', 256, 34, 3)])
 def test_recurrent_shapes(cuda, cell, H, B, T):
     """Every supported hidden size of the tcgen05 kernel (multiples of 20 up to 320), batch sizes that leave
     partial tiles, need a second tile per CTA, or a second launch (> 256), T = 1, and a size that falls back to the
-    fp32 CUDA-core kernel (H = 90: a multiple of 10, not of 20)."""
+    fp32 CUDA-core kernel (H = 90: a multiple of 10, not of 20).  The h exchange through the output planes: H % 8 == 4
+    (reverse window shifted by four columns: 100, 300, 60, 316 -- where H + 4 fills the last k-chunk exactly -- and 4),
+    H % 16 == 8 (k-step overhang into the other direction's columns: 200, 296), H a multiple of 64 (exact windows)."""
     import dl4ss_b200 as d
     try:
         rnn, ours = _rnn_pair(cell, 1, H, T)
