@@ -126,6 +126,22 @@ __device__ __forceinline__ void transpose4(float (&x)[4], int b0, int b1) {
         x[1] = selp_f(x[1], ra, b0); x[3] = selp_f(x[3], rb, b0);
     }
 }
+// The gate arithmetic is MUFU bound (EX2 + RCP per sigmoid / tanh: 10 per LSTM cell, 640 cycles per tile and step on the
+// SM's 16 lanes), so two activations share one reciprocal: 1/a and 1/b from r = 1/(a*b).  The exponents are clamped at
+// +-40 (sigmoid(-40) = 4e-18, 1 - tanh(20) = 8e-18) so that the product of two denominators stays finite.
+__device__ __forceinline__ void sigmoid2_f(float xa, float xb, float &sa, float &sb) {
+    const float da = 1.0f + __expf(-fmaxf(xa, -40.0f)), db = 1.0f + __expf(-fmaxf(xb, -40.0f));
+    const float r = __fdividef(1.0f, da * db);
+    sa = db * r;
+    sb = da * r;
+}
+__device__ __forceinline__ void sigmoid_tanh_f(float xs, float xt, float &sg, float &th) {
+    const float ds = 1.0f + __expf(-fmaxf(xs, -40.0f)), dt = 1.0f + __expf(fminf(2.0f * xt, 40.0f));
+    const float r = __fdividef(1.0f, ds * dt);
+    sg = dt * r;
+    th = fmaf(-2.0f * ds, r, 1.0f);          // 1 - 2 / (exp(2x) + 1)
+}
+
 __device__ __forceinline__ unsigned pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (unsigned)__bfloat16_as_ushort(a) | ((unsigned)__bfloat16_as_ushort(b) << 16);
 }
@@ -249,11 +265,12 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
                 const int z = (((s - 1) & 1) * 2 + dir) * 2;
                 const unsigned want = per_step * (unsigned)s;
                 if (tl == 0) stamp(p, s, 0);
+                // armed before the wait: the previous phase of every chunk barrier was consumed by the last step's UMMAs
+                for (int c = 0; c < nkc; ++c) mbar_expect_tx(&hfull[tl * RT_MAXKC + c], 2 * RT_HBLK);     // one box = both planes of the chunk
                 while (ld_acquire_gpu(ctr) < want) { __nanosleep(40); }
                 if (tl == 0) stamp(p, s, 1);
                 fence_proxy_async();             // the group's generic-proxy stores -> this thread's TMA reads
                 for (int c = 0; c < nkc; ++c) {
-                    mbar_expect_tx(&hfull[tl * RT_MAXKC + c], 2 * RT_HBLK);     // one box = both planes of the chunk
                     if (p.yx)       // rows (b, t of step s-1) of the layer output: [64 columns][1 frame][32 utterances][2 planes]
                         tma_load_4d(hs + (size_t)(c * 2) * RT_HBLK, &tmap_h, &hfull[tl * RT_MAXKC + c], ycol0 + c * RT_KC,
                                     dir ? (T - s) : (s - 1), (tile_first + tl) * RT_NT, 0);
@@ -370,18 +387,17 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if constexpr (CELL == DL4SS_CELL_LSTM) {
-                        const float ig = sigmoid_f(xv[i][0] + G4[i][0]);
-                        const float fg = sigmoid_f(xv[i][1] + G4[i][1]);
-                        const float gg = tanh_f(xv[i][2] + G4[i][2]);
-                        const float og = sigmoid_f(xv[i][3] + G4[i][3]);
+                        float ig, fg, gg, og;
+                        sigmoid2_f(xv[i][0] + G4[i][0], xv[i][1] + G4[i][1], ig, fg);
+                        sigmoid_tanh_f(xv[i][3] + G4[i][3], xv[i][2] + G4[i][2], og, gg);
                         const float c = fmaf(fg, state[i], ig * gg);
                         state[i] = c;
                         hnew[i] = og * tanh_f(c);
                         gv[i][0] = ig; gv[i][1] = fg; gv[i][2] = gg; gv[i][3] = og;
                         aux[i] = c;
                     } else {
-                        const float rg = sigmoid_f(xv[i][0] + G4[i][0]);
-                        const float zg = sigmoid_f(xv[i][1] + G4[i][1]);
+                        float rg, zg;
+                        sigmoid2_f(xv[i][0] + G4[i][0], xv[i][1] + G4[i][1], rg, zg);
                         const float hn = G4[i][2] + bhn;
                         const float ng = tanh_f(fmaf(rg, hn, xv[i][2]));
                         hnew[i] = fmaf(zg, state[i] - ng, ng);          // (1-z)*n + z*h
