@@ -49,7 +49,10 @@ def ncu_traffic(kernel_substr):
     import glob
     import re
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'full_*.md'))):
+    def tag(path):          # full_<what>_r<round><letter>.md: newest round / letter last
+        m = re.search(r'_r(\d+)([a-z]*)\.md$', path)
+        return (int(m.group(1)), m.group(2), path) if m else (0, '', path)
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'full_*.md')), key=tag):
         txt = open(path).read()
         for sec in txt.split('### ')[1:]:
             if kernel_substr not in sec.split('\n', 1)[0]:
@@ -241,22 +244,25 @@ def stage_times(sep, wav, idx, reps=3):
             Kpy = (2 * H + 63) // 64 * 64
             for li, lw in enumerate(layers):       # the same sequence rnn_forward issues, with events between the halves
                 e0, e1, e2 = ev(), ev(), ev(); e0.record()
-                x2d = inp.view(B * T, -1)
                 if M.use_tensor_cores():
-                    a_pl = planes if planes is not None else M.split_bf16(x2d)
-                    M.linear_tc(a_pl, M.weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, x2d.shape[1], out=xproj)
+                    a_pl = planes if planes is not None else M.split_bf16(inp.view(B * T, -1))
+                    M.linear_tc(a_pl, M.weight_planes(lw['wih']), lw['bias'], B * T, 2 * G * H, inp.shape[-1], out=xproj)
                 else:
-                    M.linear_fwd(x2d, lw['wih'], lw['bias'], 'none', out=xproj)
+                    M.linear_fwd(inp.view(B * T, -1), lw['wih'], lw['bias'], 'none', out=xproj)
                 e1.record()
                 planes = None
                 last = li == len(layers) - 1
                 if fuse:
                     planes = torch.empty(2, B * T, Kpy, device=x.device, dtype=torch.bfloat16)
-                    if Kpy > 2 * H:
+                    if Kpy > 2 * H and not M._RNN_YX:
                         planes[:, :, 2 * H:].zero_()
                     if last:
                         hmean = torch.empty(B, 2 * H, device=x.device)
-                y = M.recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, None, None, None, planes, hmean if last else None)
+                # as Separator.masks runs it: with the fused head the layer output exists as bf16 planes only (no fp32 copy)
+                y = M.recurrent_layer(lw, cell, xproj, B, T, H, ws, tc_rec, None, None, None, planes, hmean if last else None,
+                                      want_y=not fuse)
+                if y is None:
+                    y = M.HiddenStub((B, T, 2 * H), x.device)
                 e2.record(); torch.cuda.synchronize()
                 t['rnn_xproj'] += e0.elapsed_time(e1); t['rnn_recurrent'] += e1.elapsed_time(e2)
                 inp = y
@@ -289,7 +295,6 @@ def recurrent_concurrent_ms(sep, B, T, inflight, reps=3):
     for _ in range(inflight):
         sets.append({'xproj': torch.randn(B * T, 2 * G * H, device=dev) * 0.1,
                      'ws': M.recurrent_workspace(B, T, H, cell, True, dev),
-                     'y': torch.empty(B, T, 2 * H, device=dev),
                      'planes': torch.zeros(2, B * T, Kpy, device=dev, dtype=torch.bfloat16),
                      'stream': torch.cuda.Stream(dev)})
     best = 1e9
@@ -301,7 +306,8 @@ def recurrent_concurrent_ms(sep, B, T, inflight, reps=3):
             q['stream'].wait_event(e0)
             with torch.cuda.stream(q['stream']):
                 for lw in layers:
-                    M.recurrent_layer(lw, cell, q['xproj'], B, T, H, q['ws'], True, None, None, q['y'], q['planes'], None)
+                    # as the timed region runs it: the layer output leaves as bf16 planes only
+                    M.recurrent_layer(lw, cell, q['xproj'], B, T, H, q['ws'], True, None, None, None, q['planes'], None, want_y=False)
         for q in sets:
             cur.wait_stream(q['stream'])
         e1.record()
@@ -861,9 +867,10 @@ def main():
         roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops_sustained'],
                 'unit': 'TFLOP/s', 'frac': ach / peaks['bf16_tflops_sustained'],
                 'traffic': tr['bytes_per_launch'] if tr else None, 'traffic_source': tr['source'] if tr else None,
-                # K3 per launch: reads xproj [B,T,2,G*H] fp32, writes y [B,T,2H] fp32 and its bf16 hi/lo planes [2][B*T][Kp]
+                # K3 per launch as the product path runs it: reads xproj [B,T,2,G*H] fp32, writes the layer output as bf16 hi/lo
+                # planes [2][B*T][2H] (no fp32 copy; h is exchanged through these rows)
                 'algorithmic_bytes_per_launch': (B * (1 + W['L'] // W['hop']) * (2 * (4 if W['cell'] == 'lstm' else 3) * W['H'] * 4
-                                                 + 2 * W['H'] * 4 + 2 * ((2 * W['H'] + 63) // 64 * 64) * 2)) if dom == 'rnn_recurrent' else None,
+                                                 + 2 * (2 * W['H']) * 2)) if dom == 'rnn_recurrent' else None,
                 'peak_source': peaks['source'] + ' (sustained cuBLAS bf16; kernel timed inside a long step)',
                 'launches_per_step': n_launch, 'ms_per_step': st[dom], 'concurrent': conc,
                 'note': 'algorithmic fp32 FLOPs; every tensor-core stage runs bf16x3 (3 MMA products per fp32 product); the recurrent stage is a latency chain of T sequential steps per layer, not throughput bound (DESIGN.md 4)'}
