@@ -179,6 +179,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
     const size_t GH = (size_t)G * H;
     unsigned *counters = p.counters + (size_t)(dir * p.tiles_total + tile_first) * RT_CTR_STRIDE;
 
+    if (tid == 0) stamp(p, 0, 2);        // trace: kernel entry
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_h) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_x) : "memory");
@@ -207,18 +208,26 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
             const __nv_bfloat16 *row = p.wplanes + ((size_t)pl * 8 * H + (size_t)dir * 4 * H + 4 * u0 + (rvalid ? r : 0)) * p.Kp;
             const uint4 *src = reinterpret_cast<const uint4 *>(row);
             const uint2 *src2 = reinterpret_cast<const uint2 *>(row);       // 4 k positions each
-            for (int kk = 0; kk < p.Kp / 16; ++kk) {
-                uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-                if (rvalid) {
-                    if (!shifted) { a = __ldg(src + 2 * kk); b = __ldg(src + 2 * kk + 1); }
-                    else {
-                        const uint2 z = make_uint2(0u, 0u);
-                        const uint2 q0 = kk ? __ldg(src2 + 4 * kk - 1) : z, q1 = __ldg(src2 + 4 * kk);
-                        const uint2 q2 = __ldg(src2 + 4 * kk + 1), q3 = __ldg(src2 + 4 * kk + 2);
-                        a = make_uint4(q0.x, q0.y, q1.x, q1.y); b = make_uint4(q2.x, q2.y, q3.x, q3.y);
+            // four k steps' loads in flight before their stores (Kp is a multiple of 64): the row-per-lane reads are latency bound
+            for (int kk0 = 0; kk0 < p.Kp / 16; kk0 += 4) {
+                uint4 a[4], b[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = kk0 + j;
+                    a[j] = make_uint4(0u, 0u, 0u, 0u); b[j] = a[j];
+                    if (rvalid) {
+                        if (!shifted) { a[j] = __ldg(src + 2 * kk); b[j] = __ldg(src + 2 * kk + 1); }
+                        else {
+                            const uint2 z = make_uint2(0u, 0u);
+                            const uint2 q0 = kk ? __ldg(src2 + 4 * kk - 1) : z, q1 = __ldg(src2 + 4 * kk);
+                            const uint2 q2 = __ldg(src2 + 4 * kk + 1), q3 = __ldg(src2 + 4 * kk + 2);
+                            a[j] = make_uint4(q0.x, q0.y, q1.x, q1.y); b[j] = make_uint4(q2.x, q2.y, q3.x, q3.y);
+                        }
                     }
                 }
-                tmem_st8(ta + pl * RT_WPLANE + kk * 8, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tmem_st8(ta + pl * RT_WPLANE + (kk0 + j) * 8, a[j].x, a[j].y, a[j].z, a[j].w, b[j].x, b[j].y, b[j].z, b[j].w);
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -226,6 +235,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) stamp(p, 0, 3);        // trace: W_hh resident in tensor memory
 
     if (warp >= RT_W_MGR && warp < RT_W_MGR + RT_TILES) {
         // ================= tile manager (one warp per tile, one elected lane working): waits for the group's h_{t-1},
@@ -484,6 +494,7 @@ rnn_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) stamp(p, 0, 4);        // trace: all steps done
     if (warp == RT_W_MGR) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
