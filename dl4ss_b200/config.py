@@ -66,3 +66,4 @@ TRAIN_PERSISTENT_BPTT = True
 # bf16x3 projection kernel; False leaves them to the library GEMM (cuBLAS fp32).
 TRAIN_TC_GEMMS = True
 TRAIN_MN_GEMMS = True      # weight gradients from row-major planes (MN-major UMMA operands): no transposing split
+TRAIN_PLANES_ONLY_BPTT = __import__('os').environ.get('DL4SS_TRAIN_PLANES_ONLY', '1') != '0'   # LSTM on that path: the BPTT kernel writes the gate gradients as bf16 planes only (bias gradient from a ones column)

@@ -536,7 +536,7 @@ rnn_bwd_tc_kernel(const RnnBwdTcParams p) {
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(counter), "r"(1u) : "memory");
                 }
                 if (tr0) bm_stamp(p, s, 7);
-                if (oval) {
+                if (oval && p.dgx != nullptr) {
                     float *ox = p.dgx + row * GH + ou;
                     if constexpr (CELL == DL4SS_CELL_LSTM) {
 #pragma unroll
@@ -722,7 +722,9 @@ extern "C" int dl4ss_rnn_layer_bwd_tc(int cell, const float *dy, const float *wh
                                       const float *cell_save, const float *y, float *dgx, float *dgh, void *xplanes,
                                       int B, int T, int H, void *workspace, size_t workspace_bytes, void *stream) {
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || cell == DL4SS_CELL_GRU, "rnn_layer_bwd_tc: bad cell %d", cell);
-    DL4SS_CHECK_ARG(dy && whh && gates_save && cell_save && dgx && xplanes, "rnn_layer_bwd_tc: null operand");
+    // dgx (the fp32 copy of the gate gradients) may be NULL for the LSTM: the weight / input / bias gradients can all be
+    // taken from the bf16 planes (xplanes), and the chain then issues half as many scattered stores per step
+    DL4SS_CHECK_ARG(dy && whh && gates_save && cell_save && xplanes && (dgx || cell == DL4SS_CELL_LSTM), "rnn_layer_bwd_tc: null operand");
     DL4SS_CHECK_ARG(cell == DL4SS_CELL_LSTM || (y && dgh), "rnn_layer_bwd_tc: GRU needs y and dgh");
     DL4SS_CHECK_ARG(B >= 0 && T >= 1 && H >= 1, "rnn_layer_bwd_tc: bad B/T/H %d/%d/%d", B, T, H);
     if (!rnn_bwd_tc_supported(H, cell)) {

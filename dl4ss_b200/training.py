@@ -375,8 +375,9 @@ class TrainStep(object):
                                         _lib.stream())
             _lib.check(rc, 'dl4ss_rnn_bwd_step')
 
-    def _bptt_persistent(self, cell, st, dy, whh, B, T, H):
-        """The T-step BPTT chain of one layer as one persistent kernel (csrc/rnn_bwd.cu)."""
+    def _bptt_persistent(self, cell, st, dy, whh, B, T, H, planes_only=False):
+        """The T-step BPTT chain of one layer as one persistent kernel (csrc/rnn_bwd.cu).  planes_only (LSTM, tensor-core
+        kernel): the gate gradients leave as bf16 planes only, no fp32 copy."""
         lib = _lib.load()
         need = lib.dl4ss_rnn_bwd_workspace_bytes(B, T, H, cell)
         ws = st.get('bwd_ws')
@@ -390,7 +391,7 @@ class TrainStep(object):
                 xp = torch.zeros(xb, device=dy.device, dtype=torch.uint8)      # pad columns stay zero for good
                 st['xplanes'] = xp
             rc = lib.dl4ss_rnn_layer_bwd_tc(cell, _lib.ptr(dy), _lib.ptr(whh), _lib.ptr(st['gates']),
-                                            _lib.ptr(st['cells']), _lib.ptr(st['y']), _lib.ptr(st['dgx']),
+                                            _lib.ptr(st['cells']), _lib.ptr(st['y']), _lib.ptr(None if planes_only else st['dgx']),
                                             _lib.ptr(st['dgh']), ctypes.c_void_p(xp.data_ptr()), B, T, H,
                                             ctypes.c_void_p(ws.data_ptr()), need, _lib.stream())
             _lib.check(rc, 'dl4ss_rnn_layer_bwd_tc')
@@ -420,8 +421,16 @@ class TrainStep(object):
                       'carry': torch.empty(2, B, H, device=dev), 'dg_cur': torch.empty(2, B, G * H, device=dev),
                       'dh_rec': torch.empty(2, B, H, device=dev), 'whh': lw['whh'], 'graph': None}
             persistent = bool(config.TRAIN_PERSISTENT_BPTT) and _lib.load().dl4ss_rnn_bwd_supported(H, cell) != 0
+            # LSTM on the MN-major path: every gradient of the layer (dW_ih, dW_hh, dX and -- through a column of ones next to the
+            # layer input's planes -- the bias) is taken from the BPTT kernel's bf16 planes, so the fp32 copy is not written at all
+            nin_l = sv['x'].shape[-1]
+            planes_only = bool(
+                persistent and not gru and M.use_tensor_cores() and config.TRAIN_TC_GEMMS and config.TRAIN_MN_GEMMS
+                and getattr(config, 'TRAIN_PLANES_ONLY_BPTT', True)
+                and _lib.load().dl4ss_rnn_bwd_tc_supported(H, cell) != 0 and (G * H) % 8 == 0
+                and sv.get('x_planes') is not None and sv.get('y_planes') is not None and sv['x_planes'].shape[-1] > nin_l)
             if persistent:
-                self._bptt_persistent(cell, st, dy, lw['whh'], B, T, H)      # the whole chain in one launch
+                self._bptt_persistent(cell, st, dy, lw['whh'], B, T, H, planes_only)      # the whole chain in one launch
             elif use_graph and st['graph'] is not None:
                 st['dy'].copy_(dy)
                 st['whh'].copy_(lw['whh'])
@@ -446,7 +455,7 @@ class TrainStep(object):
             x2d = sv['x'].reshape(B * T, -1)
             dgx2d = dgx.view(B * T, 2 * G * H)
             y = sv['y']
-            db_x = dgx2d.sum(0)
+            db_x = None if planes_only else dgx2d.sum(0)
             if not gru and M.use_tensor_cores() and config.TRAIN_TC_GEMMS:
                 # LSTM: the recurrent-side gate gradients ARE dgx, so one transposed split of dgx serves dW_ih and both
                 # directions' dW_hh: the latter come out of ONE product against the time-shifted layer output
@@ -463,7 +472,15 @@ class TrainStep(object):
                     dg_pl = xp.view(torch.bfloat16).view(2, R, 2 * GHg)
                     x_pl, y_pl = sv['x_planes'], sv['y_planes']
                     nin = x2d.shape[1]
-                    dW_ih = M.linear_tc_tn(dg_pl, 0, 2 * G * H, 0, x_pl, 0, nin, 0, B, T, wa=2 * GHg, wb=nin) if GHg == G * H else None
+                    if planes_only:
+                        # bias gradient = dgates^T 1: a column of ones behind the layer input's columns (hi plane; the padding of
+                        # the lo plane is zero), one more output column of the same product
+                        x_pl[0, :, nin] = 1.0
+                        dW_ext = M.linear_tc_tn(dg_pl, 0, 2 * G * H, 0, x_pl, 0, nin + 1, 0, B, T, wa=2 * GHg, wb=nin + 1)
+                        x_pl[0, :, nin] = 0.0
+                        dW_ih, db_x = dW_ext[:, :nin], dW_ext[:, nin]
+                    else:
+                        dW_ih = M.linear_tc_tn(dg_pl, 0, 2 * G * H, 0, x_pl, 0, nin, 0, B, T, wa=2 * GHg, wb=nin) if GHg == G * H else None
                     for d, suf in enumerate(('', '_reverse')):
                         if dW_ih is None:
                             dWd = M.linear_tc_tn(dg_pl, d * GHg, G * H, 0, x_pl, 0, nin, 0, B, T, wa=2 * GHg, wb=nin)

@@ -328,7 +328,9 @@ int    dl4ss_rnn_layer_bwd(int cell, const float *dy, const float *whh, const fl
  * against a 16 x 20 output, which suits many warps issuing small MMAs, not tcgen05's single-thread 128-row UMMAs.
  * Same contract plus `xplanes`: caller-owned bf16 [2 (hi,lo)][B*T][2][GHg] (GHg = G*H rounded up to 8,
  * dl4ss_rnn_bwd_tc_xplanes_bytes() bytes, 16-byte aligned) through which the CTAs exchange the recurrent-side gate
- * gradients; the caller zero-fills it ONCE (the kernel never writes the GHg - G*H pad columns, which must be zero). */
+ * gradients; the caller zero-fills it ONCE (the kernel never writes the GHg - G*H pad columns, which must be zero).
+ * LSTM: `dgx` may be NULL -- the planes then are the only copy of the gate gradients (weight, input and bias gradients
+ * can all be taken from them); the GRU needs dgx and dgh. */
 int    dl4ss_rnn_bwd_tc_supported(int H, int cell);
 size_t dl4ss_rnn_bwd_tc_xplanes_bytes(int B, int T, int H, int cell);
 int    dl4ss_rnn_layer_bwd_tc(int cell, const float *dy, const float *whh, const float *gates_save,
